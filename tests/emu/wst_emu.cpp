@@ -1,0 +1,106 @@
+// wst_emu.cpp — TEST INFRASTRUCTURE ONLY.
+//
+// Compiles the product's kernel headers (csrc/wst_cascade.h, the very code nvcc builds for
+// sm_100a) with g++ and replays each CTA's barrier-separated phases thread by thread on the CPU.
+// It exists so that the index arithmetic of the fused kernels (digit-swapped FFT orders,
+// Hermitian half spectra, folds, shared-memory layout) can be checked against the oracle inside
+// the GPU-less build container.  It is never imported by the product package and is not a
+// fallback: wst_b200 fails loudly when libwst_b200.so / a GPU is missing.
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+#include "wst_tables.h"
+
+using namespace wst;
+
+namespace {
+
+template <class C>
+int run_cfg(int L, int max_order, int H, int W, const float* psi_hat, const float* phi_hat,
+            const float* x, int nsig, float* maps_out, std::string& err) {
+    std::vector<float> buf; TableOffsets off;
+    if (!build_tables<C>(L, psi_hat, phi_hat, buf, off, err)) return -1;
+    PlanTables pt{};
+    pt.L = L; pt.max_order = max_order; pt.K = num_coefficients(C::J, L, max_order);
+    pt.H = H; pt.W = W; pt.pad_top = (C::N - H) / 2; pt.pad_left = (C::N - W) / 2;
+    bind_tables<C>(pt, buf.data(), off);
+    std::vector<cfloat> sm(C::smem_cfloats() + 64), twsm(C::tw_total);
+    std::vector<cfloat> u0h((size_t)C::N * (C::N / 2 + 1));
+    HostExec<C::NT> ex;
+    const size_t map_sz = (size_t)pt.K * C::HOUT * C::HOUT;
+    for (int s = 0; s < nsig; ++s) {
+        // poison shared memory so that reads of never-written cells show up as NaN
+        for (auto& v : sm) v = cmake(NAN, NAN);
+        Cascade<C, HostExec<C::NT>> prog{ex, pt, sm.data(), twsm.data(), u0h.data(), maps_out + s * map_sz};
+        prog.load_twiddles();
+        prog.run(x + (size_t)s * H * W);
+    }
+    return 0;
+}
+
+std::string g_err;
+
+}  // namespace
+
+extern "C" {
+
+const char* emu_last_error() { return g_err.c_str(); }
+
+// 1-D/2-D FFT self-test hooks: forward then inverse through the digit-swapped layout.
+// data: M x M complex (interleaved), in place; dir=-1 forward (natural -> natural, via explicit un-swap), +1 inverse.
+int emu_fft2(int M, int dir, float* data) {
+    auto run = [&](auto Mc) {
+        constexpr int m = decltype(Mc)::value;
+        constexpr int P = m + 1;
+        constexpr int R1 = Fft1<m>::R1, R2 = Fft1<m>::R2;
+        std::vector<cfloat> sm((size_t)m * P), tw(m);
+        for (int k1 = 0; k1 < R1; ++k1) for (int i2 = 0; i2 < R2; ++i2) {
+            double a = -6.283185307179586 * ((i2 * k1) % m) / m;
+            tw[k1 * R2 + i2] = cmake((float)cos(a), (float)sin(a));
+        }
+        HostExec<256> ex;
+        const cfloat* in = reinterpret_cast<const cfloat*>(data);
+        cfloat* out = reinterpret_cast<cfloat*>(data);
+        if (dir < 0) {
+            for (int r = 0; r < m; ++r) for (int c = 0; c < m; ++c) sm[r * P + c] = in[r * m + c];
+            fft_lines_fwd<m, m, P, 1, 256>(ex, sm.data(), 1, 0, tw.data());   // rows
+            fft_lines_fwd<m, m, 1, P, 256>(ex, sm.data(), 1, 0, tw.data());   // columns
+            for (int k = 0; k < m; ++k) for (int l = 0; l < m; ++l) out[k * m + l] = sm[Fft1<m>::pi(k) * P + Fft1<m>::pi(l)];
+        } else {
+            for (int k = 0; k < m; ++k) for (int l = 0; l < m; ++l) sm[Fft1<m>::pi(k) * P + Fft1<m>::pi(l)] = in[k * m + l];
+            fft_lines_inv<m, m, 1, P, 256>(ex, sm.data(), 1, 0, tw.data());
+            fft_lines_inv<m, m, P, 1, 256>(ex, sm.data(), 1, 0, tw.data());
+            for (int r = 0; r < m; ++r) for (int c = 0; c < m; ++c) out[r * m + c] = sm[r * P + c];
+        }
+    };
+    switch (M) {
+#define CASE(m) case m: run(std::integral_constant<int, m>{}); return 0;
+        CASE(6) CASE(10) CASE(12) CASE(18) CASE(20) CASE(24) CASE(34) CASE(36) CASE(40) CASE(48) CASE(64) CASE(68) CASE(72)
+        CASE(80) CASE(96) CASE(136) CASE(144) CASE(160)
+#undef CASE
+    }
+    g_err = "emu_fft2: unsupported size";
+    return -2;
+}
+
+// Full cascade for nsig signals of H x W; writes maps [nsig][K][HOUT][HOUT].
+int emu_forward(int N, int J, int L, int max_order, int H, int W, const float* psi_hat,
+                const float* phi_hat, const float* x, int nsig, float* maps_out) {
+#define CFG(n, j) if (N == n && J == j) return run_cfg<Cfg<n, j>>(L, max_order, H, W, psi_hat, phi_hat, x, nsig, maps_out, g_err);
+#include "wst_configs.inc"
+#undef CFG
+    g_err = "emu_forward: unsupported (N, J)";
+    return -2;
+}
+
+int emu_query(int N, int J, int* smem_bytes, int* gp, int* hout) {
+#define CFG(n, j) if (N == n && J == j) { using C = Cfg<n, j>; *smem_bytes = (int)C::smem_bytes(); *hout = C::HOUT; \
+        for (int i = 0; i < j; ++i) gp[i] = 0; \
+        static_for<0, j>([&](auto Jc) { gp[decltype(Jc)::value] = C::GP(decltype(Jc)::value); }); return 0; }
+#include "wst_configs.inc"
+#undef CFG
+    return -2;
+}
+
+}  // extern "C"

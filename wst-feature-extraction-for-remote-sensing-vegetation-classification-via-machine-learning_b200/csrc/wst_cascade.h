@@ -1,0 +1,518 @@
+// wst_cascade.h — the fused scattering cascade for ONE (patch, channel) signal, executed by ONE CTA.
+//
+// Replaces, for a batch, the per-image / per-channel Python loop around kymatio's
+// core.scattering2d (reference call sites: src/training/train_and_save_model.py:364-376,
+// src/inference/inference.py:246-268; algorithm: SURVEY.md Appendix A.3).
+//
+// Data flow per signal (all intermediates stay in shared memory; only the half spectrum U0^ of
+// the padded input is parked in a per-CTA, L2-resident global scratch because every one of the
+// J*L first-order filters re-reads it):
+//
+//   x --reflect pad--> z0 --real 2-D FFT--> U0^                                    (once)
+//   S0      = lowpass(z0)
+//   U1[n1]  = | ifft2( fold( U0^ . psi^[n1] ) ) |            n1 = (j1, theta1)
+//   S1[n1]  = lowpass(U1)
+//   U1^     = real 2-D FFT(U1)                               (only when the parent has children)
+//   U2      = | ifft2( fold( U1^ . psi^[n2] ) ) |            j2 > j1, U1^ resident in shared memory
+//   S2      = lowpass(U2)
+//
+// Differences from the reference dataflow that keep the numbers (within fp32 rounding) but
+// remove work:
+//   * "lowpass" = phi^ multiply + Fourier fold + small inverse FFT + unpad in kymatio.  phi is an
+//     isotropic Gaussian, so phi^ is separable; the same result is a pair of small dense matrix
+//     products with Gr[hout x m], Gc[hout x m] (built on the host from phi^'s first row/column),
+//     evaluated only at the kept (un-padded) outputs.  No forward FFT of U2 is ever needed.
+//   * forward FFTs act on real data (|.|): two rows are packed into one complex row, and only the
+//     Hermitian half spectrum is kept.
+//   * the FFTs are in-place two-pass transforms n = R1*R2 whose frequency-domain side is left in
+//     digit-swapped order pi(k) = (k % R1)*R2 + k / R1; forward = natural->swapped (DIF),
+//     inverse = swapped->natural (DIT), so no pass needs a reorder or a second barrier.
+//
+// The code is written as a sequence of barrier-separated phases `ex.phase([&](int tid){...})`.
+// On the GPU a phase is the lambda + __syncthreads(); in tests/emu the same phases are replayed
+// thread by thread on the CPU to check the index arithmetic against the oracle.
+#pragma once
+#include "wst_dft.h"
+
+namespace wst {
+
+constexpr int kMaxJ = 6;
+constexpr int kSmemCfloats = 27000;      // data region budget (216,000 B) of the 227 KB a CTA may use
+
+// ------------------------------------------------------------------ 1-D factorisation n = R1*R2
+WST_CX int fft_R2(int n) {               // contiguous radix
+    if (n <= 20) return n;
+    int odd = n; while (odd % 2 == 0) odd /= 2;
+    int best = 0; long best_score = 1L << 60;
+    for (int r2 = odd; r2 <= 24 && r2 <= n; r2 *= 2) {
+        int r1 = n / r2;
+        if (r1 > 16 || r2 < 2) continue;
+        long d = (long)r2 * r2 - n;      // distance of r2 from sqrt(n), in squared units
+        if (d < 0) d = -d;
+        if (d < best_score) { best_score = d; best = r2; }
+    }
+    return best;
+}
+WST_CX int fft_R1(int n) { return fft_R2(n) > 0 ? n / fft_R2(n) : 0; }
+WST_CX bool fft_supported(int n) { return n >= 2 && n % 2 == 0 && fft_R2(n) > 0; }
+
+template <int N> struct Fft1 {
+    static constexpr int R2 = fft_R2(N);
+    static constexpr int R1 = N / R2;
+    static_assert(R2 > 0 && R1 * R2 == N, "unsupported FFT length");
+    // storage position of frequency k
+    static WST_HD int pi(int k) { if constexpr (R1 == 1) return k; else return (k % R1) * R2 + k / R1; }
+};
+
+// ------------------------------------------------------------------ geometry shared by host and device
+template <int N_, int J_, int NT_ = 512>
+struct Cfg {
+    static constexpr int N = N_, J = J_, NT = NT_;
+    static constexpr int NS = N >> J;           // side of the subsampled (still padded) output grid
+    static constexpr int HOUT = NS - 2;         // kept outputs per side after unpad [1:-1]
+    static constexpr int HP = (HOUT + 3) & ~3;  // padded to float4
+    static_assert((N >> J) << J == N, "padded size must be a multiple of 2^J");
+    static_assert(HOUT >= 1, "empty output");
+
+    static constexpr int msize(int j) { return N >> j; }
+    static constexpr int vsz(int m) { return m * (m + 1); }           // complex m x m array, odd pitch m+1
+    static constexpr int uhsz(int m) { return m * (m / 2 + 1); }       // half spectrum, pitch m/2+1
+    static constexpr int zend(int m, int gp) { return (gp - 1) * vsz(m) + (m / 2) * (m + 1); }
+
+    // children group size for child side mc when `room` cfloats are free below the parents' U^ arrays
+    static constexpr int pick_group(int mc, int room) {
+        for (int g = 8; g > 1; g /= 2) if (g * vsz(mc) <= room) return g;
+        return 1;
+    }
+    static constexpr bool has_children(int j) { return j < J - 1; }
+    static constexpr int level_total(int j, int gp) {
+        int m = msize(j);
+        if (!has_children(j)) return gp * vsz(m);
+        int room = kSmemCfloats - gp * uhsz(m);
+        if (room < zend(m, gp)) return 1 << 30;
+        int offb = zend(m, gp);
+        for (int j2 = j + 1; j2 < J; ++j2) {
+            int ch = pick_group(msize(j2), room) * vsz(msize(j2));
+            if (ch > room) return 1 << 30;
+            if (ch > offb) offb = ch;
+        }
+        int t = offb + gp * uhsz(m);
+        return t > gp * vsz(m) ? t : gp * vsz(m);
+    }
+    // number of same-scale parents processed together at level j
+    static constexpr int GP(int j) {
+        for (int g = 8; g > 1; g /= 2) if (level_total(j, g) <= kSmemCfloats) return g;
+        return 1;
+    }
+    static constexpr int G2(int j1, int j2) {   // children group size
+        return pick_group(msize(j2), kSmemCfloats - GP(j1) * uhsz(msize(j1)));
+    }
+    static constexpr int OFFB(int j) {          // offset of the parents' half spectra
+        int gp = GP(j), m = msize(j);
+        int offb = zend(m, gp);
+        for (int j2 = j + 1; j2 < J; ++j2) offb = cx_max(offb, G2(j, j2) * vsz(msize(j2)));
+        return offb;
+    }
+    static constexpr int smem_cfloats() {
+        int t = 0;
+        for (int j = 0; j < J; ++j) t = cx_max(t, level_total(j, GP(j)));
+        // input stage uses level-0 layout with one array
+        t = cx_max(t, cx_max(vsz(N) / 2 + 1, OFFB(0) + uhsz(N)));
+        return t;
+    }
+    static constexpr int tw_offset(int j) {     // twiddle tables, one per level, appended after the data
+        int o = 0;
+        for (int i = 0; i < j; ++i) o += msize(i);
+        return o;
+    }
+    static constexpr int tw_total = 2 * N;      // sum_j N>>j < 2N
+    static constexpr size_t smem_bytes() { return (size_t)(smem_cfloats() + tw_total) * sizeof(cfloat); }
+    static_assert(level_total(0, 1) <= kSmemCfloats, "padded size too large for the shared-memory cascade");
+};
+
+// ------------------------------------------------------------------ device-side plan tables
+struct PlanTables {
+    int L, max_order, K;
+    int H, W, pad_top, pad_left;           // un-padded input size and reflect-pad offsets
+    const cfloat* tw[kMaxJ];               // tw[j][k1*R2+i2] = exp(-2 pi i * i2*k1 / m_j)
+    const float* gr[kMaxJ];                // row   low-pass operator, [m_j][HP]  (x-major)
+    const float* gc[kMaxJ];                // column low-pass operator, [m_j][HP]
+    const float* psi1[kMaxJ];              // order-1 filters of scale j at level 0: [ceil(L/GP)][N][N][GP]
+    const float* psi2[kMaxJ][kMaxJ];       // [j2][j1]: scale-j2 filters at level j1: [ceil(L/G)][m][m][G]
+};
+
+// ------------------------------------------------------------------ executors
+#ifdef __CUDACC__
+struct DevExec {
+    template <class F> WST_D void phase(F&& f) { f((int)threadIdx.x); __syncthreads(); }
+};
+#endif
+template <int NT> struct HostExec {
+    template <class F> void phase(F&& f) { for (int t = 0; t < NT; ++t) f(t); }
+};
+
+// ------------------------------------------------------------------ FFT passes over shared memory
+// A "line set": narr arrays (stride AS), NL lines per array (stride LS), elements of a line ES apart.
+// Lanes run across lines, so both column transforms (LS = 1) and row transforms (LS = odd pitch)
+// are bank-conflict free for 64-bit accesses.
+
+// radix-R1 butterflies over elements {k1*R2 + i2}, optional twiddle after the butterfly.
+template <int M, int DIR, bool TW, int NL, int LS, int ES, int NT>
+WST_D void pass_strided(int tid, cfloat* base, int narr, int AS, const cfloat* tw) {
+    constexpr int R1 = Fft1<M>::R1, R2 = Fft1<M>::R2;
+    const int total = narr * R2 * NL;
+    for (int b = tid; b < total; b += NT) {
+        int line = b % NL, r = b / NL;
+        int i2 = r % R2, g = r / R2;
+        cfloat* p = base + g * AS + line * LS + i2 * ES;
+        cfloat a[R1];
+        static_for<0, R1>([&](auto K) { constexpr int k = decltype(K)::value; a[k] = p[k * R2 * ES]; });
+        dft<R1, DIR>(a);
+        static_for<0, R1>([&](auto K) {
+            constexpr int k = decltype(K)::value;
+            cfloat v = a[k];
+            if constexpr (TW && k > 0) {
+                cfloat w = tw[k * R2 + i2];
+                v = (DIR < 0) ? cmul(v, w) : cmulc(v, w);
+            }
+            p[k * R2 * ES] = v;
+        });
+    }
+}
+
+// radix-R2 butterflies over contiguous elements {k1*R2 + i2}, optional twiddle after.
+template <int M, int DIR, bool TW, int NL, int LS, int ES, int NT>
+WST_D void pass_contig(int tid, cfloat* base, int narr, int AS, const cfloat* tw) {
+    constexpr int R1 = Fft1<M>::R1, R2 = Fft1<M>::R2;
+    const int total = narr * R1 * NL;
+    for (int b = tid; b < total; b += NT) {
+        int line = b % NL, r = b / NL;
+        int k1 = r % R1, g = r / R1;
+        cfloat* p = base + g * AS + line * LS + k1 * R2 * ES;
+        cfloat v[R2];
+        static_for<0, R2>([&](auto I) { constexpr int i = decltype(I)::value; v[i] = p[i * ES]; });
+        dft<R2, DIR>(v);
+        static_for<0, R2>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            cfloat o = v[i];
+            if constexpr (TW && R1 > 1 && i > 0) {
+                cfloat w = tw[k1 * R2 + i];
+                o = (DIR < 0) ? cmul(o, w) : cmulc(o, w);
+            }
+            p[i * ES] = o;
+        });
+    }
+}
+
+// forward 1-D transforms of all lines: natural -> digit-swapped
+template <int M, int NL, int LS, int ES, int NT, class Exec>
+WST_D void fft_lines_fwd(Exec& ex, cfloat* base, int narr, int AS, const cfloat* tw) {
+    if constexpr (Fft1<M>::R1 > 1) {
+        ex.phase([&](int tid) { pass_strided<M, -1, true, NL, LS, ES, NT>(tid, base, narr, AS, tw); });
+    }
+    ex.phase([&](int tid) { pass_contig<M, -1, false, NL, LS, ES, NT>(tid, base, narr, AS, tw); });
+}
+
+// inverse 1-D transforms of all lines: digit-swapped -> natural (unnormalised)
+template <int M, int NL, int LS, int ES, int NT, class Exec>
+WST_D void fft_lines_inv(Exec& ex, cfloat* base, int narr, int AS, const cfloat* tw) {
+    ex.phase([&](int tid) { pass_contig<M, +1, true, NL, LS, ES, NT>(tid, base, narr, AS, tw); });
+    if constexpr (Fft1<M>::R1 > 1) {
+        ex.phase([&](int tid) { pass_strided<M, +1, false, NL, LS, ES, NT>(tid, base, narr, AS, tw); });
+    }
+}
+
+// Last pass of the inverse row transform fused with modulus and row pairing:
+//   z[x][y] = ( |u[x][y]|, |u[x + M/2][y]| ),  x < M/2, written over row x of the same array.
+template <int M, int NT>
+WST_D void pass_rows_final_modulus(int tid, cfloat* base, int narr, int AS, const cfloat* tw) {
+    constexpr int R1 = Fft1<M>::R1, R2 = Fft1<M>::R2, P = M + 1, HALF = M / 2;
+    if constexpr (R1 > 1) {
+        const int total = narr * R2 * HALF;
+        for (int b = tid; b < total; b += NT) {
+            int x = b % HALF, r = b / HALF;
+            int i2 = r % R2, g = r / R2;
+            cfloat* p0 = base + g * AS + x * P + i2;
+            cfloat* p1 = p0 + HALF * P;
+            cfloat a[R1], c[R1];
+            static_for<0, R1>([&](auto K) { constexpr int k = decltype(K)::value; a[k] = p0[k * R2]; c[k] = p1[k * R2]; });
+            dft<R1, +1>(a);
+            dft<R1, +1>(c);
+            static_for<0, R1>([&](auto K) {
+                constexpr int k = decltype(K)::value;
+                p0[k * R2] = cmake(cabs_(a[k]), cabs_(c[k]));
+            });
+        }
+    } else {   // single-pass length: the whole row transform happens here
+        const int total = narr * HALF;
+        for (int b = tid; b < total; b += NT) {
+            int x = b % HALF, g = b / HALF;
+            cfloat* p0 = base + g * AS + x * P;
+            cfloat* p1 = p0 + HALF * P;
+            cfloat a[R2], c[R2];
+            static_for<0, R2>([&](auto I) { constexpr int i = decltype(I)::value; a[i] = p0[i]; c[i] = p1[i]; });
+            dft<R2, +1>(a);
+            dft<R2, +1>(c);
+            static_for<0, R2>([&](auto I) {
+                constexpr int i = decltype(I)::value;
+                p0[i] = cmake(cabs_(a[i]), cabs_(c[i]));
+            });
+        }
+    }
+}
+
+// Inverse 2-D FFT of narr digit-swapped M x M spectra (pitch M+1) + modulus + row pairing.
+template <int M, int NT, class Exec>
+WST_D void ifft2_modulus_pair(Exec& ex, cfloat* base, int narr, const cfloat* tw) {
+    constexpr int P = M + 1, AS = M * (M + 1);
+    fft_lines_inv<M, M, 1, P, NT>(ex, base, narr, AS, tw);              // columns (along rows index)
+    if constexpr (Fft1<M>::R1 > 1) {
+        ex.phase([&](int tid) { pass_contig<M, +1, true, M, P, 1, NT>(tid, base, narr, AS, tw); });
+    }
+    ex.phase([&](int tid) { pass_rows_final_modulus<M, NT>(tid, base, narr, AS, tw); });
+}
+
+// Real 2-D forward FFT of narr paired-row arrays z (stride ZS, pitch M+1, M/2 rows) into
+// half spectra U^[pi(k)][l], l = 0..M/2 (stride UHS = M*(M/2+1), pitch M/2+1).
+template <int M, int NT, class Exec>
+WST_D void rfft2_from_pairs(Exec& ex, cfloat* z, int ZS, cfloat* uh, int narr, const cfloat* tw) {
+    constexpr int P = M + 1, HALF = M / 2, PH = M / 2 + 1, UHS = M * PH;
+    // rows of z (along y): natural -> swapped
+    fft_lines_fwd<M, HALF, P, 1, NT>(ex, z, narr, ZS, tw);
+    // split the packed rows:  A = FFT(row x), B = FFT(row x + M/2)
+    ex.phase([&](int tid) {
+        const int total = narr * PH * HALF;
+        for (int b = tid; b < total; b += NT) {
+            int x = b % HALF, r = b / HALF;
+            int l = r % PH, g = r / PH;
+            const cfloat* zr = z + g * ZS + x * P;
+            cfloat zl = zr[Fft1<M>::pi(l)];
+            cfloat zm = zr[Fft1<M>::pi(l == 0 ? 0 : M - l)];
+            cfloat A = cmake(0.5f * (zl.x + zm.x), 0.5f * (zl.y - zm.y));
+            cfloat B = cmake(0.5f * (zl.y + zm.y), -0.5f * (zl.x - zm.x));
+            cfloat* u = uh + g * UHS + l;
+            u[x * PH] = A;
+            u[(x + HALF) * PH] = B;
+        }
+    });
+    // columns of U^ (along rows index): natural -> swapped
+    fft_lines_fwd<M, PH, 1, PH, NT>(ex, uh, narr, UHS, tw);
+}
+
+// Hermitian lookup U(k, l) from a half spectrum stored as [pi(k)][l], l <= M/2.
+template <int M>
+WST_D cfloat herm_get(const cfloat* uh, int k, int l) {
+    constexpr int PH = M / 2 + 1;
+    if (l <= M / 2) return uh[Fft1<M>::pi(k) * PH + l];
+    int kk = (k == 0) ? 0 : M - k;
+    cfloat v = uh[Fft1<M>::pi(kk) * PH + (M - l)];
+    return cmake(v.x, -v.y);
+}
+
+// V_g = fold( U . psi_g ) for the GS filters of one theta-group, written digit-swapped and
+// pre-scaled by 1/(F^2 * MC^2) (fold mean and inverse-FFT normalisation).
+//   uh   : parent half spectrum, side MP (shared or global memory)
+//   filt : [MP][MP][GS] real filters of this group
+//   out  : GS arrays of MC x MC (pitch MC+1, stride MC*(MC+1))
+template <int MP, int MC, int GS, int NT>
+WST_D void product_fold(int tid, const cfloat* uh, const float* filt, cfloat* out) {
+    constexpr int F = MP / MC, PC = MC + 1, AS = MC * (MC + 1);
+    constexpr float scale = 1.0f / ((float)F * (float)F * (float)MC * (float)MC);
+    for (int o = tid; o < MC * MC; o += NT) {
+        int lc = o % MC, kc = o / MC;
+        float ar[GS], ai[GS];
+        static_for<0, GS>([&](auto G) { ar[decltype(G)::value] = 0.f; ai[decltype(G)::value] = 0.f; });
+        for (int a = 0; a < F; ++a) {
+            int k = kc + a * MC;
+            for (int b = 0; b < F; ++b) {
+                int l = lc + b * MC;
+                cfloat u = herm_get<MP>(uh, k, l);
+                const float* fp = filt + ((size_t)k * MP + l) * GS;
+                float w[GS];
+                if constexpr (GS % 4 == 0) {
+                    static_for<0, GS / 4>([&](auto Q) {
+                        constexpr int q = decltype(Q)::value;
+                        float4 t = *reinterpret_cast<const float4*>(fp + 4 * q);
+                        w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+                    });
+                } else if constexpr (GS == 2) {
+                    float2 t = *reinterpret_cast<const float2*>(fp);
+                    w[0] = t.x; w[1] = t.y;
+                } else {
+                    static_for<0, GS>([&](auto G) { w[decltype(G)::value] = fp[decltype(G)::value]; });
+                }
+                static_for<0, GS>([&](auto G) {
+                    constexpr int g = decltype(G)::value;
+                    ar[g] += u.x * w[g];
+                    ai[g] += u.y * w[g];
+                });
+            }
+        }
+        cfloat* op = out + Fft1<MC>::pi(kc) * PC + Fft1<MC>::pi(lc);
+        static_for<0, GS>([&](auto G) {
+            constexpr int g = decltype(G)::value;
+            op[g * AS] = cmake(ar[g] * scale, ai[g] * scale);
+        });
+    }
+}
+
+// Separable low-pass + subsample + unpad of narr paired-row arrays z (stride ZS, pitch M+1):
+//   S[i][i'] = sum_{x,y} Gr[x][i] * U[x][y] * Gc[y][i'],  i, i' < HOUT
+// written to maps + coef(g)*HOUT*HOUT for arrays with coef(g) >= 0.
+// Scratch: the dead second half of each array (rows >= M/2).
+template <int M, int HOUT, int HP, int NT, class Exec, class CoefFn>
+WST_D void lowpass_maps(Exec& ex, cfloat* z, int ZS, int narr, const float* gr, const float* gc,
+                        float* maps, CoefFn coef) {
+    constexpr int P = M + 1, HALF = M / 2;
+    // chunks of the x range per (array, y) so that about NT threads are busy; scratch must fit
+    constexpr int NCH_FIT = (M + 1) / HOUT < 1 ? 1 : (M + 1) / HOUT;
+    const int want = (NT + narr * M - 1) / (narr * M);
+    const int nch = want < 1 ? 1 : (want > NCH_FIT ? NCH_FIT : (want > HALF ? HALF : want));
+    const int xper = (HALF + nch - 1) / nch;
+    ex.phase([&](int tid) {
+        const int total = narr * nch * M;
+        for (int b = tid; b < total; b += NT) {
+            int y = b % M, r = b / M;
+            int c = r % nch, g = r / nch;
+            const cfloat* zp = z + g * ZS + y;
+            float acc[HOUT];
+            static_for<0, HOUT>([&](auto I) { acc[decltype(I)::value] = 0.f; });
+            int x0 = c * xper, x1 = x0 + xper < HALF ? x0 + xper : HALF;
+            for (int x = x0; x < x1; ++x) {
+                cfloat v = zp[x * P];
+                const float* g0 = gr + x * HP;
+                const float* g1 = gr + (x + HALF) * HP;
+                static_for<0, HP / 4>([&](auto Q) {
+                    constexpr int q = decltype(Q)::value;
+                    float4 a = *reinterpret_cast<const float4*>(g0 + 4 * q);
+                    float4 d = *reinterpret_cast<const float4*>(g1 + 4 * q);
+                    if constexpr (4 * q + 0 < HOUT) acc[4 * q + 0] += a.x * v.x + d.x * v.y;
+                    if constexpr (4 * q + 1 < HOUT) acc[4 * q + 1] += a.y * v.x + d.y * v.y;
+                    if constexpr (4 * q + 2 < HOUT) acc[4 * q + 2] += a.z * v.x + d.z * v.y;
+                    if constexpr (4 * q + 3 < HOUT) acc[4 * q + 3] += a.w * v.x + d.w * v.y;
+                });
+            }
+            float* tp = reinterpret_cast<float*>(z + g * ZS + HALF * P) + (c * HOUT) * M + y;
+            static_for<0, HOUT>([&](auto I) { tp[decltype(I)::value * M] = acc[decltype(I)::value]; });
+        }
+    });
+    ex.phase([&](int tid) {
+        const int total = narr * HOUT * HOUT;
+        for (int b = tid; b < total; b += NT) {
+            int ic = b % HOUT, r = b / HOUT;
+            int ir = r % HOUT, g = r / HOUT;
+            int cidx = coef(g);
+            if (cidx < 0) continue;
+            const float* tp = reinterpret_cast<const float*>(z + g * ZS + HALF * P) + ir * M;
+            float s = 0.f;
+            for (int y = 0; y < M; ++y) {
+                float t = tp[y];
+                for (int c = 1; c < nch; ++c) t += tp[c * HOUT * M + y];
+                s += t * gc[y * HP + ic];
+            }
+            maps[(size_t)cidx * (HOUT * HOUT) + ir * HOUT + ic] = s;
+        }
+    });
+}
+
+// ------------------------------------------------------------------ the per-signal program
+template <class C, class Exec>
+struct Cascade {
+    static constexpr int N = C::N, J = C::J, NT = C::NT, HOUT = C::HOUT, HP = C::HP;
+
+    Exec& ex;
+    const PlanTables& pt;
+    cfloat* sm;          // shared data region (C::smem_cfloats())
+    cfloat* twsm;        // shared twiddles   (C::tw_total)
+    cfloat* u0h;         // per-CTA global scratch: N * (N/2+1)
+    float* maps;         // this signal's output maps [K][HOUT][HOUT]
+
+    WST_D const cfloat* tw(int j) const { return twsm + C::tw_offset(j); }
+
+    // index of the first order-2 coefficient of parent (j1, t1)
+    WST_D int order2_base(int j1, int t1) const {
+        int L = pt.L, idx = 1 + J * L;
+        for (int j = 0; j < j1; ++j) idx += L * L * (J - 1 - j);
+        return idx + t1 * L * (J - 1 - j1);
+    }
+
+    // once per CTA
+    WST_D void load_twiddles() {
+        ex.phase([&](int tid) {
+            static_for<0, J>([&](auto Jj) {
+                constexpr int j = decltype(Jj)::value;
+                constexpr int m = C::msize(j);
+                for (int i = tid; i < m; i += NT) twsm[C::tw_offset(j) + i] = pt.tw[j][i];
+            });
+        });
+    }
+
+    // reflect-pad the H x W input into paired rows z0, S0, and U0^ -> global scratch
+    WST_D void input_stage(const float* x) {
+        constexpr int P = N + 1, HALF = N / 2, PH = N / 2 + 1;
+        const int H = pt.H, W = pt.W, pt_top = pt.pad_top, pt_left = pt.pad_left;
+        ex.phase([&](int tid) {
+            for (int o = tid; o < HALF * N; o += NT) {
+                int c = o % N, r = o / N;
+                int sc = c - pt_left; sc = sc < 0 ? -sc : (sc >= W ? 2 * (W - 1) - sc : sc);
+                int r0 = r - pt_top; r0 = r0 < 0 ? -r0 : (r0 >= H ? 2 * (H - 1) - r0 : r0);
+                int r1 = r + HALF - pt_top; r1 = r1 < 0 ? -r1 : (r1 >= H ? 2 * (H - 1) - r1 : r1);
+                sm[r * P + c] = cmake(x[r0 * W + sc], x[r1 * W + sc]);
+            }
+        });
+        lowpass_maps<N, HOUT, HP, NT>(ex, sm, 0, 1, pt.gr[0], pt.gc[0], maps, [](int) { return 0; });
+        cfloat* uh = sm + C::OFFB(0);
+        rfft2_from_pairs<N, NT>(ex, sm, 0, uh, 1, tw(0));
+        ex.phase([&](int tid) {
+            for (int o = tid; o < N * PH; o += NT) u0h[o] = uh[o];
+        });
+    }
+
+    template <int J1, int J2>
+    WST_D void children(const cfloat* uh_parent, int t1) {
+        constexpr int MP = C::msize(J1), MC = C::msize(J2), G = C::G2(J1, J2);
+        const int L = pt.L;
+        const int ngroups = (L + G - 1) / G;
+        const int cbase = order2_base(J1, t1) + (J2 - J1 - 1) * L;
+        for (int grp = 0; grp < ngroups; ++grp) {
+            const float* filt = pt.psi2[J2][J1] + (size_t)grp * MP * MP * G;
+            ex.phase([&](int tid) { product_fold<MP, MC, G, NT>(tid, uh_parent, filt, sm); });
+            ifft2_modulus_pair<MC, NT>(ex, sm, G, tw(J2));
+            lowpass_maps<MC, HOUT, HP, NT>(ex, sm, C::vsz(MC), G, pt.gr[J2], pt.gc[J2], maps,
+                                           [&](int g) { int t2 = grp * G + g; return t2 < L ? cbase + t2 : -1; });
+        }
+    }
+
+    template <int J1>
+    WST_D void level() {
+        constexpr int M = C::msize(J1), GPn = C::GP(J1);
+        const int L = pt.L;
+        const int ngroups = (L + GPn - 1) / GPn;
+        for (int grp = 0; grp < ngroups; ++grp) {
+            const float* filt = pt.psi1[J1] + (size_t)grp * N * N * GPn;
+            ex.phase([&](int tid) { product_fold<N, M, GPn, NT>(tid, u0h, filt, sm); });
+            ifft2_modulus_pair<M, NT>(ex, sm, GPn, tw(J1));
+            lowpass_maps<M, HOUT, HP, NT>(ex, sm, C::vsz(M), GPn, pt.gr[J1], pt.gc[J1], maps,
+                                          [&](int g) { int t1 = grp * GPn + g; return t1 < L ? 1 + J1 * L + t1 : -1; });
+            if constexpr (C::has_children(J1)) {
+                if (pt.max_order >= 2) {
+                    cfloat* uh = sm + C::OFFB(J1);
+                    rfft2_from_pairs<M, NT>(ex, sm, C::vsz(M), uh, GPn, tw(J1));
+                    for (int g = 0; g < GPn; ++g) {
+                        int t1 = grp * GPn + g;
+                        if (t1 >= L) break;
+                        const cfloat* uhp = uh + g * C::uhsz(M);
+                        static_for<J1 + 1, J>([&](auto J2c) { this->template children<J1, decltype(J2c)::value>(uhp, t1); });
+                    }
+                }
+            }
+        }
+    }
+
+    WST_D void run(const float* x) {
+        input_stage(x);
+        static_for<0, J>([&](auto Jc) { this->template level<decltype(Jc)::value>(); });
+    }
+};
+
+}  // namespace wst
