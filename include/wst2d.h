@@ -1,0 +1,84 @@
+/* wst2d.h — C ABI of libwst_b200.so: batched 2-D wavelet scattering features on one B200.
+ *
+ * The reference (a pure-Python repo) has no FFI for this path; the interface it exposes is the
+ * Python call surface below, and these entry points are what a ctypes binding for that surface
+ * binds (INTEGRATION.md shows the stub):
+ *
+ *   reference interface replaced                                   entry point
+ *   -------------------------------------------------------------  ---------------------------
+ *   kymatio `Scattering2D(J, shape, L, max_order)` constructed at   wst2d_plan_create
+ *     src/training/train_and_save_model.py:359,
+ *     src/inference/inference.py:242,
+ *     src/visualization/visualize_features.py:210,
+ *     src/visualization/compare_wst_coefficients.py:37
+ *   `scattering(channel)` + np.mean/np.std over (-2,-1) at          wst2d_forward (features),
+ *     src/training/train_and_save_model.py:368-372,                 wst2d_forward (maps != NULL)
+ *     src/inference/inference.py:254-266,                             for the coefficient maps of
+ *     src/visualization/visualize_features.py:213-217                 visualize_features.py:222
+ *   `load_rgb_image` uint8 HWC -> float32/255 CHW at                wst2d_forward_u8
+ *     src/training/train_and_save_model.py:51-56
+ *
+ * All pointers are plain device or host pointers; no torch types.  Every function returns 0 on
+ * success or a negative code, and wst2d_last_error() (thread-local) describes the failure.
+ * There is no CPU fallback: creating a plan without a usable CUDA device fails with
+ * WST2D_ERR_CUDA.
+ */
+#ifndef WST2D_H
+#define WST2D_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct wst2d_plan wst2d_plan;
+
+#define WST2D_OK            0
+#define WST2D_ERR_ARG      (-1)   /* bad argument (NULL, non-positive size, 2^J > min(H,W), ...) */
+#define WST2D_ERR_UNSUPPORTED (-2) /* no compiled cascade for this (padded size, J) */
+#define WST2D_ERR_CUDA     (-3)   /* CUDA runtime error, or no device */
+
+/* Build the filter bank and tables for `Scattering2D(J, shape=(H, W), L, max_order)` on `device`.
+ * Geometry follows kymatio: padded side ((M + 2^J) / 2^J + 1) * 2^J, reflect padding,
+ * K = 1 + L*J + L^2*J*(J-1)/2 coefficients (1 + L*J when max_order == 1),
+ * output maps (H_p / 2^J - 2) x (W_p / 2^J - 2). */
+int wst2d_plan_create(wst2d_plan** out, int device, int H, int W, int J, int L, int max_order);
+int wst2d_plan_destroy(wst2d_plan* plan);
+
+/* Geometry of a plan; any output pointer may be NULL. */
+int wst2d_query(const wst2d_plan* plan, int* K, int* h, int* w, int* Hp, int* Wp);
+
+/* x_dev: [B][C][H][W] float32, contiguous, on the plan's device.
+ * feats_dev: [B][C][2][K] float32 — per (patch, channel): mean(K) then population std(K) of each
+ *            coefficient map over its h x w pixels (the training layout of
+ *            train_and_save_model.py:371-376 once flattened per patch).  May be NULL.
+ * maps_dev:  [B][C][K][h][w] float32 coefficient maps, or NULL.
+ * Work is enqueued on `cuda_stream` (a cudaStream_t; NULL = default stream) without host sync. */
+int wst2d_forward(const wst2d_plan* plan, const float* x_dev, int64_t B, int C,
+                  float* feats_dev, float* maps_dev, void* cuda_stream);
+
+/* Same, from uint8 pixels: x_dev is [B][H][W][C] uint8 (PIL / load_rgb_image order); the /255
+ * scaling and the HWC -> CHW transpose happen on the device. */
+int wst2d_forward_u8(const wst2d_plan* plan, const uint8_t* x_dev, int64_t B, int C,
+                     float* feats_dev, float* maps_dev, void* cuda_stream);
+
+/* Host-buffer convenience path (what a drop-in extractor calls): x_host [B][C][H][W] float32 and
+ * feats_host [B][C][2][K] live in host memory (pinned for full overlap); copies are chunked and
+ * double-buffered against compute on two internal streams.  Synchronous on return. */
+int wst2d_forward_host(const wst2d_plan* plan, const float* x_host, int64_t B, int C, float* feats_host);
+
+/* Debug/test export of the plan's full-resolution Fourier-domain filters, host pointers:
+ * psi_hat [J*L][Hp][Wp], phi_hat [Hp][Wp]; either may be NULL. */
+int wst2d_plan_filters(const wst2d_plan* plan, float* psi_hat, float* phi_hat);
+
+/* Number of kernels wst2d_forward launches for a batch of B*C signals (for launch accounting). */
+int wst2d_launch_count(const wst2d_plan* plan, int64_t B, int C);
+
+const char* wst2d_last_error(void);
+const char* wst2d_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WST2D_H */

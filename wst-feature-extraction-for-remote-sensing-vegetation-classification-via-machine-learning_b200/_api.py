@@ -1,0 +1,345 @@
+"""Host-side mirror of the reference's WST interface, backed by libwst_b200.so (sm_100a CUDA).
+
+Reference surfaces mirrored:
+  B3  kymatio `Scattering2D(J, shape, L=8, max_order=2, ...)`  -> Scattering2D (numpy / torch flavours)
+  B1  extract_wst_features(rgb_image)            train_and_save_model.py:346-378  (block layout)
+  B2  ModelInference.extract_wst_features(...)   inference.py:237-270             (interleaved layout)
+      extract_wst_features(grayscale_image)      visualize_features.py:194-222    (features, maps)
+      compute_scattering_coefficients(img, L, J) compare_wst_coefficients.py:35-39
+  B4  batched op scattering_features / scattering_maps on CUDA tensors (what the kernels sit behind)
+
+torch is used for device memory and streams only.  There is no CPU fallback: without the CUDA
+library or a GPU every entry point raises.
+"""
+import ctypes
+import threading
+
+import numpy as np
+import torch
+
+from . import _lib
+
+__all__ = [
+    "Plan", "get_plan", "scattering_features", "scattering_maps", "features_from_host",
+    "Scattering2D", "ScatteringNumPy2D", "ScatteringTorch2D",
+    "extract_wst_features", "extract_wst_features_interleaved", "extract_wst_features_gray",
+    "compute_scattering_coefficients", "extract_wst_features_batch", "num_coefficients",
+    "compute_padding", "to_interleaved", "to_block",
+]
+
+
+# ----------------------------------------------------------------------------- geometry
+def compute_padding(M, N, J):
+    """kymatio scattering2d/utils.py::compute_padding."""
+    return ((M + 2 ** J) // 2 ** J + 1) * 2 ** J, ((N + 2 ** J) // 2 ** J + 1) * 2 ** J
+
+
+def num_coefficients(J, L=8, max_order=2):
+    K = 1 + L * J
+    if max_order >= 2:
+        K += L * L * J * (J - 1) // 2
+    return K
+
+
+# ----------------------------------------------------------------------------- plan
+class Plan:
+    """Owns a wst2d_plan (filter bank + tables on one device) for Scattering2D(J, shape, L, max_order)."""
+
+    def __init__(self, H, W, J, L=8, max_order=2, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("wst_b200: no CUDA device available (this package has no CPU fallback).")
+        lib = _lib.load()
+        self.device = torch.cuda.current_device() if device is None else torch.device(device).index or 0
+        self.H, self.W, self.J, self.L, self.max_order = int(H), int(W), int(J), int(L), int(max_order)
+        h = ctypes.c_void_p()
+        _lib.check(lib.wst2d_plan_create(ctypes.byref(h), self.device, self.H, self.W, self.J, self.L,
+                                         self.max_order))
+        self._h = h
+        q = [ctypes.c_int() for _ in range(5)]
+        _lib.check(lib.wst2d_query(h, *[ctypes.byref(v) for v in q]))
+        self.K, self.h, self.w, self.Hp, self.Wp = [v.value for v in q]
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                _lib.load().wst2d_plan_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # -- device path -------------------------------------------------------------------------
+    def _check_x(self, x):
+        if not isinstance(x, torch.Tensor):
+            raise TypeError("The input should be a PyTorch Tensor.")
+        if x.dim() != 4:
+            raise RuntimeError("Input tensor must be [B, C, H, W].")
+        if x.shape[-2] != self.H or x.shape[-1] != self.W:
+            raise RuntimeError("Tensor must be of spatial size (%i,%i)." % (self.H, self.W))
+        if not x.is_cuda or x.device.index != self.device:
+            raise RuntimeError("Input tensor must live on cuda:%d." % self.device)
+        if not x.is_contiguous():
+            raise RuntimeError("Tensor must be contiguous.")
+
+    def forward(self, x, want_features=True, want_maps=False):
+        """x: [B, C, H, W] float32 (or uint8 [B, H, W, C]) CUDA tensor -> (feats [B, C, 2, K] | None, maps | None)."""
+        lib = _lib.load()
+        u8 = x.dtype == torch.uint8
+        if u8:
+            if x.dim() != 4 or x.shape[1] != self.H or x.shape[2] != self.W:
+                raise RuntimeError("uint8 input must be [B, H, W, C] of spatial size (%i,%i)." % (self.H, self.W))
+            if not x.is_cuda or not x.is_contiguous():
+                raise RuntimeError("uint8 input must be a contiguous CUDA tensor.")
+            B, C = x.shape[0], x.shape[3]
+        else:
+            self._check_x(x)
+            if x.dtype != torch.float32:
+                raise TypeError("Input tensor must be float32 (or uint8 HWC).")
+            B, C = x.shape[0], x.shape[1]
+        feats = torch.empty((B, C, 2, self.K), dtype=torch.float32, device=x.device) if want_features else None
+        maps = torch.empty((B, C, self.K, self.h, self.w), dtype=torch.float32, device=x.device) if want_maps else None
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        fn = lib.wst2d_forward_u8 if u8 else lib.wst2d_forward
+        _lib.check(fn(self._h, x.data_ptr(), B, C,
+                      feats.data_ptr() if feats is not None else None,
+                      maps.data_ptr() if maps is not None else None,
+                      ctypes.c_void_p(stream)))
+        return feats, maps
+
+    # -- host path ---------------------------------------------------------------------------
+    def forward_host(self, x, out=None):
+        """x: [B, C, H, W] float32 C-contiguous numpy array or CPU tensor (pinned for full overlap)
+        -> feats [B, C, 2, K] numpy float32.  Copies are chunked and overlapped inside the library."""
+        lib = _lib.load()
+        if isinstance(x, torch.Tensor):
+            xa = x.numpy()
+        else:
+            xa = x
+        if xa.dtype != np.float32 or not xa.flags["C_CONTIGUOUS"] or xa.ndim != 4:
+            raise RuntimeError("forward_host expects a C-contiguous float32 [B, C, H, W] array.")
+        if xa.shape[-2] != self.H or xa.shape[-1] != self.W:
+            raise RuntimeError("NumPy array must be of spatial size (%i,%i)." % (self.H, self.W))
+        B, C = xa.shape[0], xa.shape[1]
+        if out is None:
+            out = np.empty((B, C, 2, self.K), np.float32)
+        oa = out.numpy() if isinstance(out, torch.Tensor) else out
+        _lib.check(lib.wst2d_forward_host(self._h, xa.ctypes.data, B, C, oa.ctypes.data))
+        return out
+
+    def filters(self):
+        """(psi_hat [J*L, Hp, Wp], phi_hat [Hp, Wp]) float32 — the plan's full-resolution filter bank."""
+        psi = np.empty((self.J * self.L, self.Hp, self.Wp), np.float32)
+        phi = np.empty((self.Hp, self.Wp), np.float32)
+        _lib.check(_lib.load().wst2d_plan_filters(self._h, psi.ctypes.data, phi.ctypes.data))
+        return psi, phi
+
+    def launch_count(self, B, C):
+        return int(_lib.load().wst2d_launch_count(self._h, B, C))
+
+
+_PLAN_CACHE = {}
+_PLAN_LOCK = threading.Lock()
+
+
+def get_plan(H, W, J, L=8, max_order=2, device=None):
+    """Plan cache keyed (device, H, W, J, L, max_order): the filter bank is built once, not per image
+    (the reference rebuilds it per image, train_and_save_model.py:359 — SURVEY.md F5)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("wst_b200: no CUDA device available (this package has no CPU fallback).")
+    dev = torch.cuda.current_device() if device is None else (torch.device(device).index or 0)
+    key = (dev, int(H), int(W), int(J), int(L), int(max_order))
+    with _PLAN_LOCK:
+        p = _PLAN_CACHE.get(key)
+        if p is None:
+            p = Plan(H, W, J, L, max_order, dev)
+            _PLAN_CACHE[key] = p
+        return p
+
+
+# ----------------------------------------------------------------------------- layouts
+def to_interleaved(feats_block):
+    """[..., C, 2, K] (mean block, std block) -> [..., C*2*K] interleaved [mean0, std0, mean1, ...]
+    (inference.py:263-266)."""
+    f = feats_block
+    f = f.swapaxes(-1, -2) if isinstance(f, np.ndarray) else f.transpose(-1, -2)
+    return f.reshape(f.shape[:-3] + (-1,))
+
+
+def to_block(feats_block):
+    """[..., C, 2, K] -> [..., C*2*K] per channel [mean(K) || std(K)] (train_and_save_model.py:375)."""
+    return feats_block.reshape(feats_block.shape[:-3] + (-1,))
+
+
+# ----------------------------------------------------------------------------- batched device op (B4)
+def scattering_features(x, J, L=8, max_order=2, layout="block"):
+    """x: [B, C, H, W] float32 CUDA tensor -> [B, C*2*K] pooled features on the same device."""
+    plan = get_plan(x.shape[-2], x.shape[-1], J, L, max_order, x.device)
+    feats, _ = plan.forward(x, want_features=True)
+    return to_block(feats) if layout == "block" else to_interleaved(feats).contiguous()
+
+
+def scattering_maps(x, J, L=8, max_order=2):
+    """x: [B, C, H, W] float32 CUDA tensor -> coefficient maps [B, C, K, h, w]."""
+    plan = get_plan(x.shape[-2], x.shape[-1], J, L, max_order, x.device)
+    _, maps = plan.forward(x, want_features=False, want_maps=True)
+    return maps
+
+
+def features_from_host(x, J, L=8, max_order=2, layout="block", device=None):
+    """x: [B, C, H, W] float32 host array -> [B, C*2*K] numpy features (host in, host out)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    plan = get_plan(x.shape[-2], x.shape[-1], J, L, max_order, device)
+    feats = plan.forward_host(x)
+    return to_block(feats) if layout == "block" else np.ascontiguousarray(to_interleaved(feats))
+
+
+# ----------------------------------------------------------------------------- Scattering2D frontends (B3)
+class _ScatteringBase2D:
+    def __init__(self, J, shape, L=8, max_order=2, pre_pad=False, backend=None, out_type="array"):
+        self.J, self.shape, self.L, self.max_order = J, tuple(shape), L, max_order
+        self.pre_pad, self.backend, self.out_type = pre_pad, backend, out_type
+        M, N = self.shape
+        if 2 ** J > M or 2 ** J > N:
+            raise RuntimeError("The smallest dimension should be larger than 2^J.")
+        if pre_pad:
+            raise NotImplementedError("wst_b200: pre_pad=True is not supported.")
+        if out_type not in ("array", "list"):
+            raise RuntimeError("The out_type must be one of 'array' or 'list'.")
+        self._M_padded, self._N_padded = compute_padding(M, N, J)
+        self._plan = None
+
+    def _get_plan(self, device=None):
+        if self._plan is None or (device is not None and self._plan.device != (torch.device(device).index or 0)):
+            self._plan = get_plan(self.shape[0], self.shape[1], self.J, self.L, self.max_order, device)
+        return self._plan
+
+    def _meta(self):
+        """kymatio's out_type='list' metadata, in output order."""
+        J, L = self.J, self.L
+        out = [{"j": (), "n": (), "theta": ()}]
+        for n1 in range(J * L):
+            out.append({"j": (n1 // L,), "n": (n1,), "theta": (n1 % L,)})
+        if self.max_order >= 2:
+            for n1 in range(J * L):
+                for n2 in range(J * L):
+                    if n2 // L > n1 // L:
+                        out.append({"j": (n1 // L, n2 // L), "n": (n1, n2), "theta": (n1 % L, n2 % L)})
+        return out
+
+
+class ScatteringNumPy2D(_ScatteringBase2D):
+    """Drop-in for `kymatio.numpy.Scattering2D`: ndarray[..., H, W] -> ndarray[..., K, h, w]."""
+
+    def scattering(self, input):
+        if not type(input) is np.ndarray:
+            raise TypeError("The input should be a NumPy array.")
+        if len(input.shape) < 2:
+            raise RuntimeError("Input array must have at least two dimensions.")
+        if input.shape[-1] != self.shape[-1] or input.shape[-2] != self.shape[-2]:
+            raise RuntimeError("NumPy array must be of spatial size (%i,%i)." % (self.shape[0], self.shape[1]))
+        batch_shape = input.shape[:-2]
+        out_dtype = input.dtype if input.dtype in (np.float32, np.float64) else np.float32
+        x = np.ascontiguousarray(input.reshape((-1, 1) + input.shape[-2:]), dtype=np.float32)
+        plan = self._get_plan()
+        xd = torch.from_numpy(x).to("cuda:%d" % plan.device)
+        _, maps = plan.forward(xd, want_features=False, want_maps=True)
+        S = maps[:, 0].cpu().numpy().astype(out_dtype, copy=False)
+        S = S.reshape(batch_shape + S.shape[-3:])
+        if self.out_type == "list":
+            meta = self._meta()
+            return [dict(coef=S[..., i, :, :], **meta[i]) for i in range(S.shape[-3])]
+        return S
+
+    __call__ = scattering
+
+
+class ScatteringTorch2D(torch.nn.Module, _ScatteringBase2D):
+    """Drop-in for `kymatio.torch.Scattering2D`: Tensor[..., H, W] -> Tensor[..., K, h, w].
+    CPU tensors are moved to the GPU and the result is moved back (inference.py:250-257 feeds CPU tensors)."""
+
+    def __init__(self, J, shape, L=8, max_order=2, pre_pad=False, backend=None, out_type="array"):
+        torch.nn.Module.__init__(self)
+        _ScatteringBase2D.__init__(self, J, shape, L, max_order, pre_pad, backend, out_type)
+
+    def scattering(self, input):
+        if not torch.is_tensor(input):
+            raise TypeError("The input should be a PyTorch Tensor.")
+        if len(input.shape) < 2:
+            raise RuntimeError("Input tensor must have at least two dimensions.")
+        if not input.is_contiguous():
+            raise RuntimeError("Tensor must be contiguous.")
+        if input.shape[-1] != self.shape[-1] or input.shape[-2] != self.shape[-2]:
+            raise RuntimeError("Tensor must be of spatial size (%i,%i)." % (self.shape[0], self.shape[1]))
+        batch_shape = input.shape[:-2]
+        x = input.reshape((-1, 1) + tuple(input.shape[-2:]))
+        dev = input.device if input.is_cuda else None
+        plan = self._get_plan(dev)
+        xd = x.to(device="cuda:%d" % plan.device, dtype=torch.float32).contiguous()
+        with torch.no_grad():
+            _, maps = plan.forward(xd, want_features=False, want_maps=True)
+        S = maps[:, 0].to(device=input.device, dtype=input.dtype if input.dtype.is_floating_point else torch.float32)
+        S = S.reshape(tuple(batch_shape) + tuple(S.shape[-3:]))
+        if self.out_type == "list":
+            meta = self._meta()
+            return [dict(coef=S[..., i, :, :], **meta[i]) for i in range(S.shape[-3])]
+        return S
+
+    forward = scattering
+
+
+def Scattering2D(J, shape, L=8, max_order=2, pre_pad=False, backend=None, out_type="array", frontend="numpy"):
+    """Drop-in for `kymatio.Scattering2D(..., frontend=...)` (compare_wst_coefficients.py:37)."""
+    if frontend == "numpy":
+        return ScatteringNumPy2D(J, shape, L, max_order, pre_pad, backend, out_type)
+    if frontend == "torch":
+        return ScatteringTorch2D(J, shape, L, max_order, pre_pad, backend, out_type)
+    raise RuntimeError("The frontend '%s' is not valid. Must be one of 'numpy' or 'torch'." % frontend)
+
+
+# ----------------------------------------------------------------------------- reference extractors (B1, B2)
+def extract_wst_features(rgb_image, J=2, L=8, max_order=2):
+    """Drop-in for train_and_save_model.py:346-378: float32 [C, H, W] -> float32 [C*2*K],
+    per channel [mean(K) || std(K)], channels concatenated.  J=2, L=8 are the reference's constants."""
+    rgb_image = np.asarray(rgb_image)
+    if rgb_image.ndim != 3:
+        raise ValueError("rgb_image must be [C, H, W]")
+    x = np.ascontiguousarray(rgb_image[None], dtype=np.float32)
+    plan = get_plan(x.shape[-2], x.shape[-1], J, L, max_order)
+    feats = plan.forward_host(x)                       # [1, C, 2, K]
+    return feats.reshape(-1)
+
+
+def extract_wst_features_interleaved(rgb_image, J=2, L=8):
+    """Drop-in for inference.py:237-270: float32 [C, H, W] -> float64 [C*2*K],
+    per channel [mean0, std0, mean1, std1, ...]."""
+    rgb_image = np.asarray(rgb_image)
+    x = np.ascontiguousarray(rgb_image[None], dtype=np.float32)
+    plan = get_plan(x.shape[-2], x.shape[-1], J, L, 2)
+    feats = plan.forward_host(x)[0]                    # [C, 2, K]
+    return np.ascontiguousarray(feats.swapaxes(-1, -2)).reshape(-1).astype(np.float64)
+
+
+def extract_wst_features_gray(grayscale_image, J=2, L=8):
+    """Drop-in for visualize_features.py:194-222: [H, W] -> (features [2K], coefficient maps [K, h, w]),
+    dtype following the input like kymatio (float64 in -> float64 out)."""
+    g = np.asarray(grayscale_image)
+    out_dtype = g.dtype if g.dtype in (np.float32, np.float64) else np.float32
+    H, W = g.shape
+    plan = get_plan(H, W, J, L, 2)
+    xd = torch.from_numpy(np.ascontiguousarray(g[None, None], dtype=np.float32)).to("cuda:%d" % plan.device)
+    feats, maps = plan.forward(xd, want_features=True, want_maps=True)
+    return (feats[0, 0].reshape(-1).cpu().numpy().astype(out_dtype),
+            maps[0, 0].cpu().numpy().astype(out_dtype))
+
+
+def compute_scattering_coefficients(img_tensor, L=6, J=3):
+    """Drop-in for compare_wst_coefficients.py:35-39 (note the sign flip kept from the reference)."""
+    scattering = Scattering2D(J=J, shape=img_tensor.shape, L=L, max_order=2, frontend="numpy")
+    return -scattering(img_tensor)
+
+
+def extract_wst_features_batch(images, J=2, L=8, max_order=2, layout="block"):
+    """Batched form of extract_wst_features: [B, C, H, W] host array -> [B, C*2*K] float32,
+    row b identical to extract_wst_features(images[b]) (the per-image loop at
+    train_and_save_model.py:486-490 collapses into one call)."""
+    return features_from_host(images, J, L, max_order, layout)

@@ -1,0 +1,55 @@
+"""ctypes binding of libwst_b200.so (include/wst2d.h).  Fails loudly if the library is missing."""
+import ctypes
+import os
+
+from ._build import LIB_PATH
+
+WST2D_OK, WST2D_ERR_ARG, WST2D_ERR_UNSUPPORTED, WST2D_ERR_CUDA = 0, -1, -2, -3
+
+# every symbol include/wst2d.h declares
+SYMBOLS = ["wst2d_plan_create", "wst2d_plan_destroy", "wst2d_query", "wst2d_forward", "wst2d_forward_u8",
+           "wst2d_forward_host", "wst2d_plan_filters", "wst2d_launch_count", "wst2d_last_error",
+           "wst2d_version"]
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "wst_b200: %s is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+    lib.wst2d_plan_create.argtypes = [ctypes.POINTER(vp), i32, i32, i32, i32, i32, i32]
+    lib.wst2d_plan_destroy.argtypes = [vp]
+    lib.wst2d_query.argtypes = [vp] + [ctypes.POINTER(i32)] * 5
+    lib.wst2d_forward.argtypes = [vp, vp, i64, i32, vp, vp, vp]
+    lib.wst2d_forward_u8.argtypes = [vp, vp, i64, i32, vp, vp, vp]
+    lib.wst2d_forward_host.argtypes = [vp, vp, i64, i32, vp]
+    lib.wst2d_plan_filters.argtypes = [vp, vp, vp]
+    lib.wst2d_launch_count.argtypes = [vp, i64, i32]
+    lib.wst2d_last_error.restype = ctypes.c_char_p
+    lib.wst2d_version.restype = ctypes.c_char_p
+    for name in SYMBOLS:
+        if name not in ("wst2d_last_error", "wst2d_version"):
+            getattr(lib, name).restype = i32
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load().wst2d_last_error().decode("utf-8", "replace")
+
+
+def check(rc):
+    """Map C-ABI return codes to the exceptions kymatio's frontends raise."""
+    if rc == WST2D_OK:
+        return
+    msg = last_error()
+    if rc == WST2D_ERR_UNSUPPORTED:
+        raise NotImplementedError("wst_b200: " + msg)
+    raise RuntimeError(msg if rc == WST2D_ERR_ARG else "wst_b200: " + msg)

@@ -74,18 +74,18 @@ struct Cfg {
     static_assert((N >> J) << J == N, "padded size must be a multiple of 2^J");
     static_assert(HOUT >= 1, "empty output");
 
-    static constexpr int msize(int j) { return N >> j; }
-    static constexpr int vsz(int m) { return m * (m + 1); }           // complex m x m array, odd pitch m+1
-    static constexpr int uhsz(int m) { return m * (m / 2 + 1); }       // half spectrum, pitch m/2+1
-    static constexpr int zend(int m, int gp) { return (gp - 1) * vsz(m) + (m / 2) * (m + 1); }
+    static WST_CX int msize(int j) { return N >> j; }
+    static WST_CX int vsz(int m) { return m * (m + 1); }           // complex m x m array, odd pitch m+1
+    static WST_CX int uhsz(int m) { return m * (m / 2 + 1); }       // half spectrum, pitch m/2+1
+    static WST_CX int zend(int m, int gp) { return (gp - 1) * vsz(m) + (m / 2) * (m + 1); }
 
     // children group size for child side mc when `room` cfloats are free below the parents' U^ arrays
-    static constexpr int pick_group(int mc, int room) {
+    static WST_CX int pick_group(int mc, int room) {
         for (int g = 8; g > 1; g /= 2) if (g * vsz(mc) <= room) return g;
         return 1;
     }
-    static constexpr bool has_children(int j) { return j < J - 1; }
-    static constexpr int level_total(int j, int gp) {
+    static WST_CX bool has_children(int j) { return j < J - 1; }
+    static WST_CX int level_total(int j, int gp) {
         int m = msize(j);
         if (!has_children(j)) return gp * vsz(m);
         int room = kSmemCfloats - gp * uhsz(m);
@@ -100,33 +100,33 @@ struct Cfg {
         return t > gp * vsz(m) ? t : gp * vsz(m);
     }
     // number of same-scale parents processed together at level j
-    static constexpr int GP(int j) {
+    static WST_CX int GP(int j) {
         for (int g = 8; g > 1; g /= 2) if (level_total(j, g) <= kSmemCfloats) return g;
         return 1;
     }
-    static constexpr int G2(int j1, int j2) {   // children group size
+    static WST_CX int G2(int j1, int j2) {   // children group size
         return pick_group(msize(j2), kSmemCfloats - GP(j1) * uhsz(msize(j1)));
     }
-    static constexpr int OFFB(int j) {          // offset of the parents' half spectra
+    static WST_CX int OFFB(int j) {          // offset of the parents' half spectra
         int gp = GP(j), m = msize(j);
         int offb = zend(m, gp);
         for (int j2 = j + 1; j2 < J; ++j2) offb = cx_max(offb, G2(j, j2) * vsz(msize(j2)));
         return offb;
     }
-    static constexpr int smem_cfloats() {
+    static WST_CX int smem_cfloats() {
         int t = 0;
         for (int j = 0; j < J; ++j) t = cx_max(t, level_total(j, GP(j)));
         // input stage uses level-0 layout with one array
         t = cx_max(t, cx_max(vsz(N) / 2 + 1, OFFB(0) + uhsz(N)));
         return t;
     }
-    static constexpr int tw_offset(int j) {     // twiddle tables, one per level, appended after the data
+    static WST_CX int tw_offset(int j) {     // twiddle tables, one per level, appended after the data
         int o = 0;
         for (int i = 0; i < j; ++i) o += msize(i);
         return o;
     }
     static constexpr int tw_total = 2 * N;      // sum_j N>>j < 2N
-    static constexpr size_t smem_bytes() { return (size_t)(smem_cfloats() + tw_total) * sizeof(cfloat); }
+    static WST_CX size_t smem_bytes() { return (size_t)(smem_cfloats() + tw_total) * sizeof(cfloat); }
     static_assert(level_total(0, 1) <= kSmemCfloats, "padded size too large for the shared-memory cascade");
 };
 

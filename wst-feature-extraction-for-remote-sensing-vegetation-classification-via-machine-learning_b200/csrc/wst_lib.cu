@@ -1,0 +1,495 @@
+// wst_lib.cu — CUDA kernels (sm_100a) and the C ABI of libwst_b200.so (include/wst2d.h).
+//
+// Kernels:
+//   cascade_kernel<Cfg>   one persistent CTA per SM; each CTA runs the whole scattering cascade of
+//                         one (patch, channel) signal at a time out of shared memory (wst_cascade.h)
+//   pool_kernel           per-coefficient mean / population std over the h x w map, one warp per
+//                         map, warp-shuffle reductions (np.mean / np.std of
+//                         train_and_save_model.py:371-372)
+//   u8_to_chw_kernel      uint8 HWC -> float32 CHW / 255 (load_rgb_image, train...:51-56)
+//   gabor_spatial_kernel, dft_axis{0,1}_kernel, combine_filters_kernel
+//                         fp64 filter-bank construction, once per plan (wst_filters.h)
+//
+// There is no CPU fallback anywhere in this file: without a CUDA device plan creation fails.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "wst_tables.h"
+#include "wst_filters.h"
+#include "../../include/wst2d.h"
+
+using namespace wst;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return fail(WST2D_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));    \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// the fused cascade
+// ------------------------------------------------------------------------------------------------
+template <class C>
+__global__ void __launch_bounds__(C::NT, 1)
+cascade_kernel(const PlanTables pt, const float* __restrict__ x, long long nsig, cfloat* u0h_scratch,
+               float* maps) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cfloat* sm = reinterpret_cast<cfloat*>(smem_raw);
+    cfloat* twsm = sm + C::smem_cfloats();
+    DevExec ex;
+    const size_t sig_elems = (size_t)pt.H * pt.W;
+    const size_t map_elems = (size_t)pt.K * C::HOUT * C::HOUT;
+    Cascade<C, DevExec> prog{ex, pt, sm, twsm,
+                             u0h_scratch + (size_t)blockIdx.x * (C::N * (C::N / 2 + 1)), nullptr};
+    prog.load_twiddles();
+    for (long long s = blockIdx.x; s < nsig; s += gridDim.x) {
+        prog.maps = maps + (size_t)s * map_elems;
+        prog.run(x + (size_t)s * sig_elems);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pooling: one warp per coefficient map
+// ------------------------------------------------------------------------------------------------
+__global__ void pool_kernel(const float* __restrict__ maps, float* __restrict__ feats,
+                            long long nsig, int K, int npix) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const float inv = 1.0f / (float)npix;
+    for (long long m = warp; m < nsig * K; m += nwarps) {
+        const float* p = maps + (size_t)m * npix;
+        float s = 0.f;
+        for (int i = lane; i < npix; i += 32) s += p[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s * inv;
+        float v = 0.f;
+        for (int i = lane; i < npix; i += 32) { float d = p[i] - mean; v = fmaf(d, d, v); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) {
+            long long sig = m / K; int k = (int)(m - sig * K);
+            feats[(size_t)sig * 2 * K + k] = mean;
+            feats[(size_t)sig * 2 * K + K + k] = sqrtf(v * inv);
+        }
+    }
+}
+
+// uint8 [B][H][W][C] -> float32 [B][C][H][W] / 255
+__global__ void u8_to_chw_kernel(const uint8_t* __restrict__ in, float* __restrict__ out,
+                                 long long B, int C, int HW) {
+    const long long total = B * C * (long long)HW;
+    for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total;
+         o += (long long)gridDim.x * blockDim.x) {
+        long long b = o / ((long long)C * HW);
+        int r = (int)(o - b * (long long)C * HW);
+        int c = r / HW, p = r - c * HW;
+        out[o] = (float)in[(b * HW + p) * C + c] / 255.0f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// filter bank (fp64, once per plan)
+// ------------------------------------------------------------------------------------------------
+__global__ void gabor_spatial_kernel(const GaborParams* __restrict__ gp, int nf, int N, double2* out) {
+    int y = blockIdx.x * blockDim.x + threadIdx.x;
+    int x = blockIdx.y, f = blockIdx.z;
+    if (y >= N || f >= nf) return;
+    GaborParams p = gp[f];
+    double re, im;
+    gabor_point(p, x, y, N, N, re, im);
+    out[((size_t)f * N + x) * N + y] = make_double2(re, im);
+}
+
+// out[f][k][y] = sum_x W[(k*x) % N] * in[f][x][y],   W[t] = exp(-2 pi i t / N)
+__global__ void dft_axis0_kernel(const double2* __restrict__ in, double2* __restrict__ out,
+                                 const double2* __restrict__ W, int N) {
+    int y = blockIdx.x * blockDim.x + threadIdx.x;
+    int k = blockIdx.y, f = blockIdx.z;
+    if (y >= N) return;
+    const double2* p = in + (size_t)f * N * N + y;
+    double ar = 0.0, ai = 0.0;
+    int t = 0;
+    for (int x = 0; x < N; ++x) {
+        double2 w = W[t], v = p[(size_t)x * N];
+        ar += w.x * v.x - w.y * v.y;
+        ai += w.x * v.y + w.y * v.x;
+        t += k; if (t >= N) t -= N;
+    }
+    out[((size_t)f * N + k) * N + y] = make_double2(ar, ai);
+}
+
+// out[f][k][l] = sum_y in[f][k][y] * W[(l*y) % N]
+__global__ void dft_axis1_kernel(const double2* __restrict__ in, double2* __restrict__ out,
+                                 const double2* __restrict__ W, int N) {
+    int l = blockIdx.x * blockDim.x + threadIdx.x;
+    int k = blockIdx.y, f = blockIdx.z;
+    if (l >= N) return;
+    const double2* p = in + ((size_t)f * N + k) * N;
+    double ar = 0.0, ai = 0.0;
+    int t = 0;
+    for (int y = 0; y < N; ++y) {
+        double2 w = W[t], v = p[y];
+        ar += w.x * v.x - w.y * v.y;
+        ai += w.x * v.y + w.y * v.x;
+        t += l; if (t >= N) t -= N;
+    }
+    out[((size_t)f * N + k) * N + l] = make_double2(ar, ai);
+}
+
+// psi^[n] = Re(W^ - K Wmod^), K = W^[0,0]/Wmod^[0,0];  phi^ = Re(G^)
+__global__ void combine_filters_kernel(const double2* __restrict__ spec, int nwave, int N,
+                                       float* __restrict__ psi_hat, float* __restrict__ phi_hat) {
+    size_t NN = (size_t)N * N;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int n = blockIdx.y;
+    if (i >= NN) return;
+    if (n < nwave) {
+        const double2* w = spec + (size_t)(2 * n) * NN;
+        const double2* m = spec + (size_t)(2 * n + 1) * NN;
+        double2 a = w[0], b = m[0];
+        double den = b.x * b.x + b.y * b.y;
+        double kr = (a.x * b.x + a.y * b.y) / den, ki = (a.y * b.x - a.x * b.y) / den;
+        psi_hat[(size_t)n * NN + i] = (float)(w[i].x - (kr * m[i].x - ki * m[i].y));
+    } else {
+        phi_hat[i] = (float)spec[(size_t)(2 * nwave) * NN + i].x;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// configuration dispatch
+// ------------------------------------------------------------------------------------------------
+struct CfgOps {
+    int N, J, NT, hout;
+    size_t smem;
+    const void* kernel;
+    bool (*build)(int, const float*, const float*, std::vector<float>&, TableOffsets&, std::string&);
+    void (*bind)(PlanTables&, const float*, const TableOffsets&);
+    cudaError_t (*launch)(const PlanTables&, const float*, long long, cfloat*, float*, int, cudaStream_t);
+};
+
+template <class C>
+cudaError_t launch_cascade(const PlanTables& pt, const float* x, long long nsig, cfloat* u0h, float* maps,
+                           int grid, cudaStream_t st) {
+    cascade_kernel<C><<<grid, C::NT, C::smem_bytes(), st>>>(pt, x, nsig, u0h, maps);
+    return cudaGetLastError();
+}
+
+template <class C>
+CfgOps make_ops() {
+    CfgOps o;
+    o.N = C::N; o.J = C::J; o.NT = C::NT; o.hout = C::HOUT;
+    o.smem = C::smem_bytes();
+    o.kernel = (const void*)cascade_kernel<C>;
+    o.build = &build_tables<C>;
+    o.bind = &bind_tables<C>;
+    o.launch = &launch_cascade<C>;
+    return o;
+}
+
+const std::vector<CfgOps>& all_ops() {
+    static const std::vector<CfgOps> ops = {
+#define CFG(n, j) make_ops<Cfg<n, j>>(),
+#include "wst_configs.inc"
+#undef CFG
+    };
+    return ops;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+struct wst2d_plan {
+    int device = 0;
+    int H = 0, W = 0, J = 0, L = 0, max_order = 0;
+    int N = 0, K = 0, hout = 0;
+    int grid_max = 0;                 // persistent grid: SMs x resident CTAs per SM
+    const CfgOps* ops = nullptr;
+    PlanTables pt{};
+    float* d_tables = nullptr;
+    std::vector<float> psi_hat, phi_hat;   // host copies (debug export)
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int build_filter_bank_gpu(wst2d_plan* p) {
+    const int N = p->N, J = p->J, L = p->L;
+    const int nwave = J * L, nf = 2 * nwave + 1;
+    const size_t NN = (size_t)N * N;
+    std::vector<GaborParams> gp(nf);
+    bank_gabors(J, L, gp.data());
+    std::vector<double2> W(N);
+    for (int t = 0; t < N; ++t) {
+        double a = -2.0 * 3.14159265358979323846 * (double)t / (double)N;
+        W[t] = make_double2(std::cos(a), std::sin(a));
+    }
+    GaborParams* d_gp = nullptr; double2 *d_a = nullptr, *d_b = nullptr, *d_W = nullptr;
+    float *d_psi = nullptr, *d_phi = nullptr;
+    auto cleanup = [&]() { cudaFree(d_gp); cudaFree(d_a); cudaFree(d_b); cudaFree(d_W); cudaFree(d_psi); cudaFree(d_phi); };
+#define TRYC(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); \
+        return fail(WST2D_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
+    TRYC(cudaMalloc(&d_gp, nf * sizeof(GaborParams)));
+    TRYC(cudaMalloc(&d_a, nf * NN * sizeof(double2)));
+    TRYC(cudaMalloc(&d_b, nf * NN * sizeof(double2)));
+    TRYC(cudaMalloc(&d_W, N * sizeof(double2)));
+    TRYC(cudaMalloc(&d_psi, nwave * NN * sizeof(float)));
+    TRYC(cudaMalloc(&d_phi, NN * sizeof(float)));
+    TRYC(cudaMemcpy(d_gp, gp.data(), nf * sizeof(GaborParams), cudaMemcpyHostToDevice));
+    TRYC(cudaMemcpy(d_W, W.data(), N * sizeof(double2), cudaMemcpyHostToDevice));
+    dim3 blk(128), grd((N + 127) / 128, N, nf);
+    gabor_spatial_kernel<<<grd, blk>>>(d_gp, nf, N, d_a);
+    dft_axis0_kernel<<<grd, blk>>>(d_a, d_b, d_W, N);
+    dft_axis1_kernel<<<grd, blk>>>(d_b, d_a, d_W, N);
+    dim3 cg((unsigned)((NN + 255) / 256), nwave + 1);
+    combine_filters_kernel<<<cg, 256>>>(d_a, nwave, N, d_psi, d_phi);
+    TRYC(cudaGetLastError());
+    p->psi_hat.resize(nwave * NN);
+    p->phi_hat.resize(NN);
+    TRYC(cudaMemcpy(p->psi_hat.data(), d_psi, nwave * NN * sizeof(float), cudaMemcpyDeviceToHost));
+    TRYC(cudaMemcpy(p->phi_hat.data(), d_phi, NN * sizeof(float), cudaMemcpyDeviceToHost));
+#undef TRYC
+    cleanup();
+    return WST2D_OK;
+}
+
+// signals per launch when the maps go to an internal scratch (bounded to ~1 GiB)
+long long chunk_signals(const wst2d_plan* p) {
+    size_t map_bytes = (size_t)p->K * p->hout * p->hout * sizeof(float);
+    long long c = (long long)((size_t)1 << 30) / (long long)map_bytes;
+    if (c < p->grid_max) c = p->grid_max;
+    return c;
+}
+
+int forward_impl(const wst2d_plan* p, const float* x_dev, long long nsig, float* feats_dev,
+                 float* maps_dev, cudaStream_t st) {
+    if (nsig == 0) return WST2D_OK;
+    const size_t sig_elems = (size_t)p->H * p->W;
+    const size_t map_elems = (size_t)p->K * p->hout * p->hout;
+    const size_t u0h_elems = (size_t)p->N * (p->N / 2 + 1);
+    const long long chunk = maps_dev ? nsig : (nsig < chunk_signals(p) ? nsig : chunk_signals(p));
+    const int grid_all = (int)(nsig < p->grid_max ? nsig : p->grid_max);
+    cfloat* d_u0h = nullptr; float* d_maps = nullptr;
+    CUDA_TRY(cudaMallocAsync(&d_u0h, (size_t)grid_all * u0h_elems * sizeof(cfloat), st));
+    if (!maps_dev) {
+        cudaError_t e = cudaMallocAsync(&d_maps, (size_t)chunk * map_elems * sizeof(float), st);
+        if (e != cudaSuccess) { cudaFreeAsync(d_u0h, st); return fail(WST2D_ERR_CUDA, std::string("cudaMallocAsync(maps): ") + cudaGetErrorString(e)); }
+    }
+    int rc = WST2D_OK;
+    for (long long s0 = 0; s0 < nsig && rc == WST2D_OK; s0 += chunk) {
+        long long n = nsig - s0 < chunk ? nsig - s0 : chunk;
+        int grid = (int)(n < p->grid_max ? n : p->grid_max);
+        float* maps = maps_dev ? maps_dev + (size_t)s0 * map_elems : d_maps;
+        cudaError_t e = p->ops->launch(p->pt, x_dev + (size_t)s0 * sig_elems, n, d_u0h, maps, grid, st);
+        if (e != cudaSuccess) { rc = fail(WST2D_ERR_CUDA, std::string("cascade launch: ") + cudaGetErrorString(e)); break; }
+        if (feats_dev) {
+            long long nmaps = n * p->K;
+            long long blocks = (nmaps + 7) / 8;                 // 8 warps per block
+            if (blocks > 148 * 16) blocks = 148 * 16;
+            pool_kernel<<<(unsigned)blocks, 256, 0, st>>>(maps, feats_dev + (size_t)s0 * 2 * p->K, n, p->K,
+                                                          p->hout * p->hout);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) { rc = fail(WST2D_ERR_CUDA, std::string("pool launch: ") + cudaGetErrorString(e)); break; }
+        }
+    }
+    cudaFreeAsync(d_u0h, st);
+    if (d_maps) cudaFreeAsync(d_maps, st);
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* wst2d_last_error(void) { return g_last_error.c_str(); }
+const char* wst2d_version(void) { return "wst_b200 0.1 (sm_100a)"; }
+
+int wst2d_plan_create(wst2d_plan** out, int device, int H, int W, int J, int L, int max_order) {
+    if (!out) return fail(WST2D_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (H <= 0 || W <= 0 || J < 1 || J >= kMaxJ || L < 1 || L > 64 || (max_order != 1 && max_order != 2))
+        return fail(WST2D_ERR_ARG, "invalid plan arguments");
+    if ((1 << J) > H || (1 << J) > W)
+        return fail(WST2D_ERR_ARG, "The smallest dimension should be larger than 2^J.");
+    const int Hp = padded_size(H, J), Wp = padded_size(W, J);
+    const CfgOps* ops = nullptr;
+    if (Hp == Wp)
+        for (const CfgOps& o : all_ops()) if (o.N == Hp && o.J == J) { ops = &o; break; }
+    if (!ops) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "no compiled cascade for padded size %dx%d, J=%d", Hp, Wp, J);
+        return fail(WST2D_ERR_UNSUPPORTED, buf);
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(WST2D_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(WST2D_ERR_ARG, "device index out of range");
+    DeviceGuard guard(device);
+
+    wst2d_plan* p = new wst2d_plan();
+    p->device = device; p->H = H; p->W = W; p->J = J; p->L = L; p->max_order = max_order;
+    p->N = Hp; p->K = num_coefficients(J, L, max_order); p->hout = ops->hout; p->ops = ops;
+
+    int rc = build_filter_bank_gpu(p);
+    if (rc != WST2D_OK) { delete p; return rc; }
+
+    std::vector<float> buf; TableOffsets off; std::string err;
+    if (!ops->build(L, p->psi_hat.data(), p->phi_hat.data(), buf, off, err)) { delete p; return fail(WST2D_ERR_ARG, err); }
+    if (cudaMalloc(&p->d_tables, buf.size() * sizeof(float)) != cudaSuccess ||
+        cudaMemcpy(p->d_tables, buf.data(), buf.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+        std::string m = cudaGetErrorString(cudaGetLastError());
+        cudaFree(p->d_tables); delete p;
+        return fail(WST2D_ERR_CUDA, "table upload: " + m);
+    }
+    p->pt.L = L; p->pt.max_order = max_order; p->pt.K = p->K;
+    p->pt.H = H; p->pt.W = W; p->pt.pad_top = (Hp - H) / 2; p->pt.pad_left = (Wp - W) / 2;
+    ops->bind(p->pt, p->d_tables, off);
+
+    e = cudaFuncSetAttribute(ops->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ops->smem);
+    int per_sm = 0, sms = 0;
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ops->kernel, ops->NT, ops->smem);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess || per_sm < 1) {
+        std::string m = e != cudaSuccess ? cudaGetErrorString(e) : "kernel does not fit on an SM";
+        cudaFree(p->d_tables); delete p;
+        return fail(WST2D_ERR_CUDA, "cascade kernel setup: " + m);
+    }
+    p->grid_max = sms * per_sm;
+    *out = p;
+    return WST2D_OK;
+}
+
+int wst2d_plan_destroy(wst2d_plan* plan) {
+    if (!plan) return WST2D_OK;
+    DeviceGuard guard(plan->device);
+    cudaFree(plan->d_tables);
+    delete plan;
+    return WST2D_OK;
+}
+
+int wst2d_query(const wst2d_plan* p, int* K, int* h, int* w, int* Hp, int* Wp) {
+    if (!p) return fail(WST2D_ERR_ARG, "plan is NULL");
+    if (K) *K = p->K;
+    if (h) *h = p->hout;
+    if (w) *w = p->hout;
+    if (Hp) *Hp = p->N;
+    if (Wp) *Wp = p->N;
+    return WST2D_OK;
+}
+
+int wst2d_forward(const wst2d_plan* p, const float* x_dev, int64_t B, int C, float* feats_dev,
+                  float* maps_dev, void* cuda_stream) {
+    if (!p) return fail(WST2D_ERR_ARG, "plan is NULL");
+    if (B < 0 || C < 1) return fail(WST2D_ERR_ARG, "B must be >= 0 and C >= 1");
+    if (B > 0 && !x_dev) return fail(WST2D_ERR_ARG, "x_dev is NULL");
+    if (!feats_dev && !maps_dev) return fail(WST2D_ERR_ARG, "both outputs are NULL");
+    DeviceGuard guard(p->device);
+    return forward_impl(p, x_dev, (long long)B * C, feats_dev, maps_dev, (cudaStream_t)cuda_stream);
+}
+
+int wst2d_forward_u8(const wst2d_plan* p, const uint8_t* x_dev, int64_t B, int C, float* feats_dev,
+                     float* maps_dev, void* cuda_stream) {
+    if (!p) return fail(WST2D_ERR_ARG, "plan is NULL");
+    if (B < 0 || C < 1) return fail(WST2D_ERR_ARG, "B must be >= 0 and C >= 1");
+    if (B > 0 && !x_dev) return fail(WST2D_ERR_ARG, "x_dev is NULL");
+    if (!feats_dev && !maps_dev) return fail(WST2D_ERR_ARG, "both outputs are NULL");
+    if (B == 0) return WST2D_OK;
+    DeviceGuard guard(p->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t n = (size_t)B * C * p->H * p->W;
+    float* d_x = nullptr;
+    CUDA_TRY(cudaMallocAsync(&d_x, n * sizeof(float), st));
+    long long blocks = (long long)((n + 255) / 256);
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    u8_to_chw_kernel<<<(unsigned)blocks, 256, 0, st>>>(x_dev, d_x, B, C, p->H * p->W);
+    int rc = forward_impl(p, d_x, (long long)B * C, feats_dev, maps_dev, st);
+    cudaFreeAsync(d_x, st);
+    return rc;
+}
+
+int wst2d_forward_host(const wst2d_plan* p, const float* x_host, int64_t B, int C, float* feats_host) {
+    if (!p) return fail(WST2D_ERR_ARG, "plan is NULL");
+    if (B < 0 || C < 1) return fail(WST2D_ERR_ARG, "B must be >= 0 and C >= 1");
+    if (B == 0) return WST2D_OK;
+    if (!x_host || !feats_host) return fail(WST2D_ERR_ARG, "host buffer is NULL");
+    DeviceGuard guard(p->device);
+    const size_t patch_in = (size_t)C * p->H * p->W, patch_out = (size_t)C * 2 * p->K;
+    // chunk: a few persistent-grid waves per copy so that H2D, compute and D2H overlap
+    long long chunk = (long long)p->grid_max * 8 / C;
+    if (chunk < 1) chunk = 1;
+    if (chunk > B) chunk = B;
+    cudaStream_t st[2] = {nullptr, nullptr};
+    float* d_x[2] = {nullptr, nullptr}; float* d_f[2] = {nullptr, nullptr};
+    int rc = WST2D_OK;
+    auto cleanup = [&]() {
+        for (int i = 0; i < 2; ++i) {
+            if (st[i]) cudaStreamSynchronize(st[i]);
+            cudaFree(d_x[i]); cudaFree(d_f[i]);
+            if (st[i]) cudaStreamDestroy(st[i]);
+        }
+    };
+    for (int i = 0; i < 2 && rc == WST2D_OK; ++i) {
+        if (cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaMalloc(&d_x[i], chunk * patch_in * sizeof(float)) != cudaSuccess ||
+            cudaMalloc(&d_f[i], chunk * patch_out * sizeof(float)) != cudaSuccess)
+            rc = fail(WST2D_ERR_CUDA, std::string("forward_host setup: ") + cudaGetErrorString(cudaGetLastError()));
+    }
+    int it = 0;
+    for (long long b0 = 0; b0 < B && rc == WST2D_OK; b0 += chunk, ++it) {
+        long long n = B - b0 < chunk ? B - b0 : chunk;
+        int i = it & 1;
+        cudaError_t e = cudaMemcpyAsync(d_x[i], x_host + (size_t)b0 * patch_in, n * patch_in * sizeof(float),
+                                        cudaMemcpyHostToDevice, st[i]);
+        if (e != cudaSuccess) { rc = fail(WST2D_ERR_CUDA, std::string("H2D: ") + cudaGetErrorString(e)); break; }
+        rc = forward_impl(p, d_x[i], n * C, d_f[i], nullptr, st[i]);
+        if (rc != WST2D_OK) break;
+        e = cudaMemcpyAsync(feats_host + (size_t)b0 * patch_out, d_f[i], n * patch_out * sizeof(float),
+                            cudaMemcpyDeviceToHost, st[i]);
+        if (e != cudaSuccess) { rc = fail(WST2D_ERR_CUDA, std::string("D2H: ") + cudaGetErrorString(e)); break; }
+    }
+    for (int i = 0; i < 2; ++i)
+        if (st[i]) {
+            cudaError_t e = cudaStreamSynchronize(st[i]);
+            if (e != cudaSuccess && rc == WST2D_OK) rc = fail(WST2D_ERR_CUDA, std::string("forward_host sync: ") + cudaGetErrorString(e));
+        }
+    cleanup();
+    return rc;
+}
+
+int wst2d_plan_filters(const wst2d_plan* p, float* psi_hat, float* phi_hat) {
+    if (!p) return fail(WST2D_ERR_ARG, "plan is NULL");
+    if (psi_hat) std::memcpy(psi_hat, p->psi_hat.data(), p->psi_hat.size() * sizeof(float));
+    if (phi_hat) std::memcpy(phi_hat, p->phi_hat.data(), p->phi_hat.size() * sizeof(float));
+    return WST2D_OK;
+}
+
+int wst2d_launch_count(const wst2d_plan* p, int64_t B, int C) {
+    if (!p) return fail(WST2D_ERR_ARG, "plan is NULL");
+    long long nsig = (long long)B * C;
+    if (nsig <= 0) return 0;
+    long long chunk = chunk_signals(p);
+    long long nch = (nsig + chunk - 1) / chunk;
+    return (int)(2 * nch);   // cascade + pool per chunk
+}
+
+}  // extern "C"
