@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py — WST patches/s on B200 (BASELINE.json metric) for the fused sm_100a Scattering2D path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config cfg3]
+
+A "step" is one pass of the hot path (Scattering2D(J, L=8, max_order=2) + mean/std pooling) over one
+batch of synthetic RGB patches per GPU.  Default workload: BASELINE.json configs[2] — 128x128, J=4, the
+configuration the metric ("WST patches/sec at 1/2/4/8 B200") and the north-star target are quoted on —
+with a fixed per-GPU batch (weak scaling; the batch axis is sharded, no data-path collective).
+
+One JSON line on stdout (rank 0):
+  value        whole-job patches/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e          same metric through the public host API (pinned host buffers, H2D + D2H inside the timed region)
+  roofline     dominant kernel (cascade) vs the HBM roofline: algorithmic bytes (SURVEY.md 8d bytes_min) per
+               launch / live CUDA-event duration of that kernel, against MEASURED_PEAKS.json
+  fp32         the binding roofline of this path: model flops / measured FMA peak
+  cpu_baseline the oracle (NumPy/SciPy restatement of the reference's kymatio path) on the host cores,
+               bounded sample, rank 0 at N=1
+--impl reference times that CPU implementation alone on the same config/metric (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {   # name -> (M, J, L, max_order, C, default per-GPU batch)
+    "cfg1": (32, 2, 8, 2, 3, 32768),
+    "cfg2": (64, 3, 8, 2, 3, 16384),
+    "cfg3": (128, 4, 8, 2, 3, 4096),
+    "repo": (128, 2, 8, 2, 3, 4096),
+}
+WORKLOAD_NAMES = {
+    "cfg1": "Scattering2D J=2 L=8 max_order=2, 32x32 RGB patches (BASELINE configs[0])",
+    "cfg2": "Scattering2D J=3 L=8 max_order=2, 64x64 RGB patches (BASELINE configs[1])",
+    "cfg3": "Scattering2D J=4 L=8 max_order=2, 128x128 RGB patches, batch sharded across GPUs (BASELINE configs[2])",
+    "repo": "Scattering2D J=2 L=8 max_order=2, 128x128 RGB patches (the reference's own setting)",
+}
+
+
+def num_coefficients(J, L, mo):
+    return 1 + L * J + (L * L * J * (J - 1) // 2 if mo >= 2 else 0)
+
+
+def flops_model(M, J, L, C):
+    """SURVEY.md 8(d) flops_alg per patch: 10 n^2 log2 n per complex 2-D FFT + 2 flops per filter multiply."""
+    import math
+    N = ((M + 2 ** J) // 2 ** J + 1) * 2 ** J
+    n = [N >> j for j in range(J + 1)]
+    count = [1 + 2 * L] + [2 * L + 2 * L * L * j for j in range(1, J)] + [num_coefficients(J, L, 2)]
+    fft = sum(c * 10 * m * m * math.log2(m) for c, m in zip(count, n))
+    pm = n[0] ** 2
+    for j1 in range(J):
+        pm += L * n[0] ** 2 + L * n[j1] ** 2
+        for j2 in range(j1 + 1, J):
+            pm += L * L * (n[j1] ** 2 + n[j2] ** 2)
+    return C * (fft + 2 * pm)
+
+
+# ----------------------------------------------------------------------------- CPU baseline (oracle)
+_CPU_STATE = {}
+
+
+def _cpu_worker(args):
+    seed, n, M, J, L, mo, C = args
+    import numpy as np
+    from oracle import extract_wst_features_training
+    rng = np.random.default_rng(seed)
+    x = (rng.integers(0, 256, (n, C, M, M)) / 255.0).astype(np.float32)
+    for b in range(n):
+        extract_wst_features_training(x[b], J=J, L=L, max_order=mo, cache_filters=True)
+    return n
+
+
+def cpu_all_cores(M, J, L, mo, C, per_core):
+    """Amortised filter bank, one process per host core (fork; the bank is built once in the parent)."""
+    import multiprocessing as mp
+    from oracle import Scattering2D
+    Scattering2D(J=J, shape=(M, M), L=L, max_order=mo, cache_filters=True)       # warm the shared cache pre-fork
+    cores = len(os.sched_getaffinity(0))
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [(1000 + i, 1, M, J, L, mo, C) for i in range(cores)])   # warm-up
+        t0 = time.perf_counter()
+        done = sum(pool.map(_cpu_worker, [(i, per_core, M, J, L, mo, C) for i in range(cores)]))
+        dt = time.perf_counter() - t0
+    return done / dt, cores, done
+
+
+def cpu_baseline(M, J, L, mo, C):
+    """Three CPU numbers: A as-called (bank rebuilt per image, 1 thread), B amortised
+    (1 thread), C amortised on all cores.  `value` is C, the strongest CPU arm."""
+    import numpy as np
+    from oracle import extract_wst_features_training
+    rng = np.random.default_rng(0)
+    big = M >= 128
+    nA, nB = (2, 8) if big else (4, 32)
+    x = (rng.integers(0, 256, (max(nA, nB), C, M, M)) / 255.0).astype(np.float32)
+    t0 = time.perf_counter()
+    for b in range(nA):
+        extract_wst_features_training(x[b], J=J, L=L, max_order=mo, cache_filters=False)
+    a = nA / (time.perf_counter() - t0)
+    extract_wst_features_training(x[0], J=J, L=L, max_order=mo, cache_filters=True)
+    t0 = time.perf_counter()
+    for b in range(nB):
+        extract_wst_features_training(x[b], J=J, L=L, max_order=mo, cache_filters=True)
+    bb = nB / (time.perf_counter() - t0)
+    per_core = 2 if big else 8
+    c, cores, done = cpu_all_cores(M, J, L, mo, C, per_core)
+    return {
+        "value": round(c, 3), "unit": "patches/s", "cores": cores, "kind": "port",
+        "sample": "%d patches (%d per core) of the same workload, filter bank amortised, one process per core; "
+                  "oracle = NumPy/SciPy restatement of kymatio 0.3.0 (reference engine not installable)" % (done, per_core),
+        "as_called_1thread": round(a, 4), "as_called_sample": "%d patches, filter bank rebuilt per image "
+        "(train_and_save_model.py:359)" % nA,
+        "amortised_1thread": round(bb, 3), "amortised_sample": "%d patches" % nB,
+    }
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- arms
+def run_reference(args, cfg):
+    """The reference's CPU implementation of the path (oracle port), all host cores, rank 0 only."""
+    M, J, L, mo, C, _ = cfg
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    big = M >= 128
+    per_core = 1 if big else 4
+    rates, cores, done = [], 0, 0
+    for i in range(args.warmup + args.steps):
+        r, cores, done = cpu_all_cores(M, J, L, mo, C, per_core)
+        if i >= args.warmup:
+            rates.append((r, done))
+    tot = sum(d for _, d in rates)
+    secs = sum(d / r for r, d in rates)
+    value = tot / secs
+    out = {
+        "impl": "reference", "metric": "WST patches/sec", "value": round(value, 3), "unit": "patches/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(1e3 * secs / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD_NAMES[args.config], "patch": [C, M, M], "J": J, "L": L, "max_order": mo,
+                   "step": "%d patches (%d per host core) through the oracle's extract_wst_features, "
+                           "filter bank amortised" % (done, per_core)},
+        "cpu_baseline": {"value": round(value, 3), "unit": "patches/s", "cores": cores, "kind": "port",
+                         "sample": "%d steps x %d patches, one process per core" % (args.steps, done)},
+        "e2e": {"value": round(value, 3), "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def run_ours(args, cfg):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import wst_b200
+
+    M, J, L, mo, C, default_batch = cfg
+    B = args.batch or default_batch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    distributed = world > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    K = num_coefficients(J, L, mo)
+    plan = wst_b200.get_plan(M, M, J, L, mo, dev)
+    gen = torch.Generator(device=dev).manual_seed(42 + 1000 * rank)
+    x = torch.randint(0, 256, (B, C, M, M), device=dev, generator=gen, dtype=torch.int32).float().div_(255.0)
+    gather = distributed and not args.no_gather
+
+    def step():
+        feats, _ = plan.forward(x)
+        if gather:
+            wst_b200.gather_features(feats.view(B, C * 2 * K), B * world)
+        return feats
+
+    def barrier():
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    plan.profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        feats = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    cas_ms, pool_ms, cas_n = plan.profile_read()
+    plan.profile(False)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- e2e: host buffers through the public API, copies inside the timed region
+    xh = torch.empty((B, C, M, M), dtype=torch.float32).pin_memory()
+    xh.copy_(x)
+    fh = torch.empty((B, C, 2, K), dtype=torch.float32).pin_memory()
+    e2e_steps = max(1, min(args.steps, 5))
+    plan.forward_host(xh, out=fh)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        plan.forward_host(xh, out=fh)        # synchronous: H2D, kernels, D2H
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device=dev, dtype=torch.float64)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e = world * B * e2e_steps / float(t.item())
+    same = bool(torch.equal(fh.to(dev), feats))
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            hbm_peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        else:
+            hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        bytes_min = 4 * C * M * M + 4 * C * 2 * K
+        launches_per_step = cas_n / args.steps if args.steps else 0
+        avg_launch_ms = cas_ms / cas_n if cas_n else float("nan")
+        patches_per_launch = B / launches_per_step if launches_per_step else 0
+        achieved = bytes_min * patches_per_launch / (avg_launch_ms * 1e-3) / 1e9
+        traffic = None
+        prof_json = os.path.join(ROOT, "profiles", "ncu_cascade_%s.json" % args.config)
+        if os.path.exists(prof_json):
+            pj = json.load(open(prof_json))
+            if pj.get("patches_per_launch") == patches_per_launch:
+                traffic = pj.get("dram_bytes_per_launch")
+        fl = flops_model(M, J, L, C)
+        try:
+            fma_peak = wst_b200.fma_peak_tflops(local)
+        except Exception:
+            fma_peak = None
+        out = {
+            "metric": "WST patches/sec", "value": round(value, 2), "unit": "patches/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAMES[args.config], "patch": [C, M, M], "J": J, "L": L, "max_order": mo,
+                       "batch_per_gpu": B, "global_batch": B * world, "features_per_patch": C * 2 * K,
+                       "parallelism": "batch sharded x%d%s" % (world, ", NCCL all-gather of features" if gather else ""),
+                       "l2": "inputs (%d MB per step) larger than L2; no flush needed" % (B * C * M * M * 4 // 2 ** 20),
+                       "input_values": "k/255, k uniform in 0..255, generated on device, seed 42+1000*rank"},
+            "e2e": {"value": round(e2e, 2), "unit": "patches/s", "h2d_bytes_per_step": B * C * M * M * 4,
+                    "d2h_bytes_per_step": B * C * 2 * K * 4, "steps": e2e_steps,
+                    "api": "Plan.forward_host (wst2d_forward_host): pinned host in/out, chunked double-buffered copies",
+                    "matches_device_path": same},
+            "gpu_launches": args.steps * plan.launch_count(B, C),
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 3), "peak": hbm_peak, "unit": "GB/s",
+                         "frac": round(achieved / hbm_peak, 6), "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "cascade_kernel", "kernel_ms_per_launch": round(avg_launch_ms, 4),
+                         "kernel_share_of_step": round(cas_ms / ms, 4) if ms else None,
+                         "pool_kernel_share_of_step": round(pool_ms / ms, 4) if ms else None,
+                         "algorithmic_bytes_per_patch": bytes_min,
+                         "note": "fused path is fp32/shared-memory bound (SURVEY.md F3); see fp32"},
+            "fp32": {"model_flops_per_patch": fl, "achieved_tflops": round(value / world * fl / 1e12, 3),
+                     "peak_tflops": round(fma_peak, 2) if fma_peak else None,
+                     "frac": round(value / world * fl / 1e12 / fma_peak, 4) if fma_peak else None,
+                     "peak_source": "measured live: wst2d_fma_peak (FMA loop, all SMs)"},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            out["cpu_baseline"] = cpu_baseline(M, J, L, mo, C)
+        print(json.dumps(out), flush=True)
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="patches per GPU per step (default per config)")
+    ap.add_argument("--no-gather", action="store_true", help="skip the NCCL feature all-gather at N>1")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

@@ -75,6 +75,16 @@ int wst2d_plan_filters(const wst2d_plan* plan, float* psi_hat, float* phi_hat);
 /* Number of kernels wst2d_forward launches for a batch of B*C signals (for launch accounting). */
 int wst2d_launch_count(const wst2d_plan* plan, int64_t B, int C);
 
+/* Optional per-kernel timing for bench.py's roofline: when enabled, wst2d_forward records CUDA events
+ * around each launch on the caller's stream; wst2d_profile_read synchronises the device, returns the
+ * summed durations (ms) since the last read and the number of cascade launches, and resets. */
+int wst2d_profile(wst2d_plan* plan, int enable);
+int wst2d_profile_read(wst2d_plan* plan, double* cascade_ms, double* pool_ms, int* cascade_launches);
+
+/* Measured fp32 FMA rate of `device` in TFLOP/s (dependent-chain-free FMA loop on all SMs): the
+ * denominator of the compute roofline, which MEASURED_PEAKS.json does not carry. */
+int wst2d_fma_peak(int device, double* tflops);
+
 const char* wst2d_last_error(void);
 const char* wst2d_version(void);
 

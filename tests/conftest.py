@@ -1,0 +1,21 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def built_lib():
+    """libwst_b200.so, (re)built if sources are newer (nvcc cross-compiles without a GPU)."""
+    import __graft_entry__ as g
+    g.build()
+    from wst_b200 import _lib
+    return _lib.load()

@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 #include "wst_tables.h"
+#include "wst_filters.h"
 
 using namespace wst;
 
@@ -92,6 +93,43 @@ int emu_forward(int N, int J, int L, int max_order, int H, int W, const float* p
 #undef CFG
     g_err = "emu_forward: unsupported (N, J)";
     return -2;
+}
+
+// The plan's filter bank on the CPU: same per-point formula (wst_filters.h) and the same dense
+// fp64 separable DFT + combine as the CUDA kernels in wst_lib.cu.
+int emu_filter_bank(int N, int J, int L, float* psi_hat, float* phi_hat) {
+    const int nwave = J * L, nf = 2 * nwave + 1;
+    const size_t NN = (size_t)N * N;
+    std::vector<GaborParams> gp(nf);
+    bank_gabors(J, L, gp.data());
+    std::vector<double> wr(N), wi(N);
+    for (int t = 0; t < N; ++t) { double a = -2.0 * 3.14159265358979323846 * t / N; wr[t] = cos(a); wi[t] = sin(a); }
+    std::vector<double> sr(NN), si(NN), tr(NN), ti(NN);
+    std::vector<double> allr((size_t)nf * NN), alli((size_t)nf * NN);
+    for (int f = 0; f < nf; ++f) {
+        for (int x = 0; x < N; ++x) for (int y = 0; y < N; ++y) gabor_point(gp[f], x, y, N, N, sr[(size_t)x * N + y], si[(size_t)x * N + y]);
+        for (int k = 0; k < N; ++k) for (int y = 0; y < N; ++y) {
+            double ar = 0, ai = 0;
+            for (int x = 0; x < N; ++x) { int t = (k * x) % N; double vr = sr[(size_t)x * N + y], vi = si[(size_t)x * N + y];
+                ar += wr[t] * vr - wi[t] * vi; ai += wr[t] * vi + wi[t] * vr; }
+            tr[(size_t)k * N + y] = ar; ti[(size_t)k * N + y] = ai;
+        }
+        for (int k = 0; k < N; ++k) for (int l = 0; l < N; ++l) {
+            double ar = 0, ai = 0;
+            for (int y = 0; y < N; ++y) { int t = (l * y) % N; double vr = tr[(size_t)k * N + y], vi = ti[(size_t)k * N + y];
+                ar += wr[t] * vr - wi[t] * vi; ai += wr[t] * vi + wi[t] * vr; }
+            allr[f * NN + (size_t)k * N + l] = ar; alli[f * NN + (size_t)k * N + l] = ai;
+        }
+    }
+    for (int n = 0; n < nwave; ++n) {
+        const double* wR = &allr[(size_t)(2 * n) * NN]; const double* wI = &alli[(size_t)(2 * n) * NN];
+        const double* mR = &allr[(size_t)(2 * n + 1) * NN]; const double* mI = &alli[(size_t)(2 * n + 1) * NN];
+        double den = mR[0] * mR[0] + mI[0] * mI[0];
+        double kr = (wR[0] * mR[0] + wI[0] * mI[0]) / den, ki = (wI[0] * mR[0] - wR[0] * mI[0]) / den;
+        for (size_t i = 0; i < NN; ++i) psi_hat[n * NN + i] = (float)(wR[i] - (kr * mR[i] - ki * mI[i]));
+    }
+    for (size_t i = 0; i < NN; ++i) phi_hat[i] = (float)allr[(size_t)(2 * nwave) * NN + i];
+    return 0;
 }
 
 int emu_query(int N, int J, int* smem_bytes, int* gp, int* hout) {

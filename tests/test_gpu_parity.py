@@ -1,0 +1,221 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes -> libwst_b200.so), against
+the oracle on the same seeded inputs, against the committed golden vectors, and through size-independent
+properties at the BASELINE sizes.
+
+Tolerance (BASELINE.json north_star): max relative error 1e-4 in fp32 per scattering coefficient.
+Metric: |a - b| / max(|b|, tau), tau = 1e-3 * max|b| per signal, b = float64 oracle —
+orders >= 1 of flat regions are ~1e-8 rounding noise in the reference itself, hence the floor.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+CONFIGS = [(32, 2, 8), (64, 3, 8), (128, 4, 8), (128, 2, 8), (32, 3, 6)]
+
+
+def floored_rel(a, b):
+    a = np.asarray(a, np.float64).reshape(a.shape[0], -1)
+    b = np.asarray(b, np.float64).reshape(b.shape[0], -1)
+    tau = 1e-3 * np.abs(b).max(axis=1, keepdims=True)
+    return float((np.abs(a - b) / np.maximum(np.abs(b), tau)).max())
+
+
+@pytest.fixture(scope="module")
+def wst():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import wst_b200
+    from wst_b200 import _lib
+    _lib.load()                      # fails loudly if libwst_b200.so is missing
+    return wst_b200
+
+
+def oracle64(M, J, L, mo=2):
+    from oracle import Scattering2D
+    return Scattering2D(J=J, shape=(M, M), L=L, max_order=mo, precision="double", cache_filters=True)
+
+
+def test_native_library_is_loaded(wst):
+    from wst_b200._build import LIB_PATH
+    maps = open("/proc/self/maps").read()
+    assert os.path.basename(LIB_PATH) in maps
+
+
+def test_raw_c_abi_roundtrip(wst):
+    """Plain ctypes against include/wst2d.h, device pointers only, no Python wrapper in between."""
+    from wst_b200 import _lib
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    assert lib.wst2d_plan_create(ctypes.byref(h), 0, 32, 32, 2, 8, 2) == 0, lib.wst2d_last_error()
+    q = [ctypes.c_int() for _ in range(5)]
+    assert lib.wst2d_query(h, *[ctypes.byref(v) for v in q]) == 0
+    assert [v.value for v in q] == [81, 8, 8, 40, 40]
+    x = torch.rand(2, 3, 32, 32, device="cuda")
+    feats = torch.empty(2, 3, 2, 81, device="cuda")
+    maps = torch.empty(2, 3, 81, 8, 8, device="cuda")
+    assert lib.wst2d_forward(h, x.data_ptr(), 2, 3, feats.data_ptr(), maps.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    ref = oracle64(32, 2, 8)(x.cpu().numpy())
+    assert floored_rel(maps.cpu().numpy().reshape(6, -1), ref.reshape(6, -1)) <= TOL
+    assert lib.wst2d_forward(h, x.data_ptr(), 0, 3, feats.data_ptr(), None, None) == 0       # empty batch
+    assert lib.wst2d_forward(h, x.data_ptr(), 2, 3, None, None, None) == -1                   # no output
+    assert lib.wst2d_launch_count(h, 2, 3) == 2
+    assert lib.wst2d_plan_destroy(h) == 0
+
+
+@pytest.mark.parametrize("M,J,L", CONFIGS)
+def test_filter_bank_vs_oracle(wst, M, J, L):
+    plan = wst.get_plan(M, M, J, L)
+    psi, phi = plan.filters()
+    S = oracle64(M, J, L)
+    opsi = np.stack([p["levels"][0] for p in S.psi])
+    assert np.abs(psi - opsi).max() <= 1e-6 * np.abs(opsi).max()
+    assert np.abs(phi - S.phi["levels"][0]).max() <= 1e-6
+
+
+@pytest.mark.parametrize("M,J,L", CONFIGS)
+def test_maps_and_features_vs_oracle(wst, M, J, L):
+    rng = np.random.default_rng(42)
+    x = (rng.integers(0, 256, (3, 3, M, M)) / 255.0).astype(np.float32)     # uint8 grid, like load_rgb_image
+    plan = wst.get_plan(M, M, J, L)
+    feats, maps = plan.forward(torch.from_numpy(x).cuda(), True, True)
+    torch.cuda.synchronize()
+    ref = oracle64(M, J, L)(x)
+    assert tuple(maps.shape) == ref.shape
+    assert floored_rel(maps.cpu().numpy().reshape(9, -1), ref.reshape(9, -1)) <= TOL
+    f = feats.cpu().numpy()
+    assert floored_rel(f[:, :, 0].reshape(9, -1), ref.mean(axis=(-2, -1)).reshape(9, -1)) <= TOL
+    assert floored_rel(f[:, :, 1].reshape(9, -1), ref.std(axis=(-2, -1)).reshape(9, -1)) <= TOL
+
+
+@pytest.mark.parametrize("tag,J,L", [("cfg1_32_J2", 2, 8), ("cfg2_64_J3", 3, 8), ("cfg3_128_J4", 4, 8),
+                                     ("repo_128_J2", 2, 8), ("compare_32_J3_L6", 3, 6)])
+def test_golden_vectors(wst, tag, J, L):
+    g = np.load(os.path.join(GOLD, tag + ".npz"))
+    x = g["x"]                                                             # [10, M, M]: 7 reference patterns + noise
+    M = x.shape[-1]
+    plan = wst.get_plan(M, M, J, L)
+    feats, maps = plan.forward(torch.from_numpy(np.ascontiguousarray(x[:, None])).cuda(), True, "maps64" in g.files)
+    f = feats.cpu().numpy()[:, 0]
+    assert floored_rel(f[:, 0], g["mean64"]) <= TOL
+    # std of the constant-gradient / flat maps is ~0; compare with a floor tied to the mean scale
+    tau = 1e-3 * np.abs(g["mean64"]).max(axis=1, keepdims=True)
+    assert float((np.abs(f[:, 1] - g["std64"]) / np.maximum(np.abs(g["std64"]), tau)).max()) <= TOL
+    if maps is not None:
+        assert floored_rel(maps.cpu().numpy()[:, 0].reshape(10, -1), g["maps64"].reshape(10, -1)) <= TOL
+
+
+def test_max_order_1(wst):
+    x = torch.rand(2, 1, 32, 32, device="cuda")
+    p1, p2 = wst.get_plan(32, 32, 2, 8, 1), wst.get_plan(32, 32, 2, 8, 2)
+    _, m1 = p1.forward(x, False, True)
+    _, m2 = p2.forward(x, False, True)
+    assert m1.shape[2] == 17
+    assert torch.equal(m1, m2[:, :, :17])
+    ref = oracle64(32, 2, 8, 1)(x.cpu().numpy())
+    assert floored_rel(m1.cpu().numpy().reshape(2, -1), ref.reshape(2, -1)) <= TOL
+
+
+def test_reference_extractor_signatures(wst):
+    """extract_wst_features in its three reference forms + compare_wst (a5)."""
+    from oracle import (extract_wst_features_training, extract_wst_features_inference,
+                        extract_wst_features_visualization, compute_scattering_coefficients)
+    from tests import patterns
+    rgb = np.random.default_rng(5).random((3, 128, 128), dtype=np.float32)
+    nc = np.transpose(np.ascontiguousarray(np.transpose(rgb, (1, 2, 0))), (2, 0, 1))   # non-contiguous view, like :55
+    assert not nc.flags["C_CONTIGUOUS"]
+    got = wst.extract_wst_features(nc)
+    ref = extract_wst_features_training(rgb, precision="double", cache_filters=True)
+    assert got.shape == (486,) and got.dtype == np.float32
+    assert floored_rel(got[None], ref[None]) <= TOL
+    got_i = wst.extract_wst_features_interleaved(rgb, J=2, L=8)
+    assert got_i.shape == (486,) and got_i.dtype == np.float64
+    assert floored_rel(got_i[None], extract_wst_features_inference(rgb, cache_filters=True)[None]) <= TOL
+    gray = patterns.circles(128)
+    f, m = wst.extract_wst_features_gray(gray)
+    rf, rm = extract_wst_features_visualization(gray, cache_filters=True)
+    assert f.dtype == np.float64 and m.shape == (81, 32, 32) and m.dtype == np.float64
+    assert floored_rel(m[None], rm[None]) <= TOL and floored_rel(f[None], rf[None]) <= TOL
+    img = rgb[0, :32, :32].copy()
+    assert floored_rel(wst.compute_scattering_coefficients(img)[None],
+                       compute_scattering_coefficients(img, cache_filters=True)[None]) <= TOL
+
+
+def test_frontends(wst):
+    import wst_b200.numpy, wst_b200.torch
+    x = np.random.default_rng(6).random((2, 3, 32, 32), dtype=np.float32)
+    ref = oracle64(32, 2, 8)(x)
+    Sn = wst_b200.numpy.Scattering2D(J=2, shape=(32, 32))
+    y = Sn(x)
+    assert y.shape == (2, 3, 81, 8, 8) and y.dtype == np.float32
+    assert floored_rel(y.reshape(6, -1), ref.reshape(6, -1)) <= TOL
+    assert Sn(x.astype(np.float64)).dtype == np.float64
+    St = wst_b200.torch.Scattering2D(J=2, shape=(32, 32))
+    t = torch.from_numpy(x[0, 0]).unsqueeze(0).unsqueeze(0).contiguous()               # inference.py:250
+    with torch.no_grad():
+        yt = St(t)
+    assert tuple(yt.shape) == (1, 1, 81, 8, 8) and yt.device.type == "cpu"
+    assert np.array_equal(yt.numpy()[0, 0], y[0, 0])
+    yc = St(t.cuda())
+    assert yc.is_cuda and torch.equal(yc.cpu(), yt)
+    lst = wst_b200.Scattering2D(J=2, shape=(32, 32), out_type="list")(x[0, 0])
+    assert len(lst) == 81 and lst[17]["j"] == (0, 1) and np.array_equal(lst[17]["coef"], y[0, 0, 17])
+
+
+def test_edge_cases(wst):
+    plan = wst.get_plan(32, 32, 2, 8)
+    f, _ = plan.forward(torch.empty(0, 3, 32, 32, device="cuda"))
+    assert tuple(f.shape) == (0, 3, 2, 81)
+    x = torch.rand(5, 4, 32, 32, device="cuda")                                          # C=4 (multispectral), ragged vs grid
+    f4, _ = plan.forward(x)
+    f1 = torch.cat([plan.forward(x[:, c:c + 1].contiguous())[0] for c in range(4)], dim=1)
+    assert torch.equal(f4, f1)
+    # constant image: S0 = c*pi/3.1415, everything else ~0 (Appendix A.4 item 2)
+    c = 0.37
+    _, m = plan.forward(torch.full((1, 1, 32, 32), c, device="cuda"), False, True)
+    m = m.cpu().numpy()[0, 0]
+    np.testing.assert_allclose(m[0], c * np.pi / 3.1415, rtol=5e-6)
+    assert np.abs(m[1:]).max() < 1e-5 * c
+    with pytest.raises(RuntimeError, match="spatial size"):
+        plan.forward(torch.rand(1, 1, 16, 16, device="cuda"))
+    with pytest.raises(NotImplementedError):
+        wst.get_plan(100, 100, 2, 8)
+
+
+def test_u8_ingest_equals_float_path(wst):
+    u8 = torch.randint(0, 256, (3, 32, 32, 3), dtype=torch.uint8, device="cuda")
+    plan = wst.get_plan(32, 32, 2, 8)
+    fu, _ = plan.forward(u8)
+    xf = (u8.permute(0, 3, 1, 2).float() / 255.0).contiguous()
+    ff, _ = plan.forward(xf)
+    assert torch.equal(fu, ff)
+
+
+@pytest.mark.parametrize("M,J", [(64, 3), (128, 4)])
+def test_full_size_properties(wst, M, J):
+    """Size-independent properties at the BASELINE sizes on a batch spanning several persistent-grid waves."""
+    plan = wst.get_plan(M, M, J, 8)
+    B = 200
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = (torch.randint(0, 256, (B, 3, M, M), device="cuda", generator=g).float() / 255.0)
+    f, _ = plan.forward(x)
+    assert torch.isfinite(f).all()
+    # batch equivalence: any sub-batch gives bit-identical rows (each signal is independent)
+    idx = torch.tensor([0, 57, 199], device="cuda")
+    fs, _ = plan.forward(x[idx].contiguous())
+    assert torch.equal(fs, f[idx])
+    # positive homogeneity S(a x) = a S(x)
+    f2, _ = plan.forward((0.5 * x[:8]).contiguous())
+    assert floored_rel((2 * f2).cpu().numpy().reshape(8, -1), f[:8].cpu().numpy().reshape(8, -1)) <= 1e-5
+    # host path is the same computation
+    fh = plan.forward_host(x[:16].cpu().numpy())
+    assert np.array_equal(fh, f[:16].cpu().numpy())
+    # checksum against the oracle on a sample
+    ref = oracle64(M, J, 8)(x[idx].cpu().numpy())
+    assert floored_rel(fs[:, :, 0].cpu().numpy().reshape(3, -1), ref.mean(axis=(-2, -1)).reshape(3, -1)) <= TOL

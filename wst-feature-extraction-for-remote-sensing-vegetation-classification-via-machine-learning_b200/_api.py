@@ -18,13 +18,14 @@ import numpy as np
 import torch
 
 from . import _lib
+from ._parallel import shard_range, shard_sizes, gather_features
 
 __all__ = [
     "Plan", "get_plan", "scattering_features", "scattering_maps", "features_from_host",
     "Scattering2D", "ScatteringNumPy2D", "ScatteringTorch2D",
     "extract_wst_features", "extract_wst_features_interleaved", "extract_wst_features_gray",
     "compute_scattering_coefficients", "extract_wst_features_batch", "num_coefficients",
-    "compute_padding", "to_interleaved", "to_block",
+    "compute_padding", "to_interleaved", "to_block", "shard_range", "shard_sizes", "gather_features", "fma_peak_tflops",
 ]
 
 
@@ -136,6 +137,15 @@ class Plan:
     def launch_count(self, B, C):
         return int(_lib.load().wst2d_launch_count(self._h, B, C))
 
+    def profile(self, enable=True):
+        _lib.check(_lib.load().wst2d_profile(self._h, 1 if enable else 0))
+
+    def profile_read(self):
+        """(cascade_ms, pool_ms, cascade_launches) summed since the last read; synchronises the device."""
+        c, p, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
+        _lib.check(_lib.load().wst2d_profile_read(self._h, ctypes.byref(c), ctypes.byref(p), ctypes.byref(n)))
+        return c.value, p.value, n.value
+
 
 _PLAN_CACHE = {}
 _PLAN_LOCK = threading.Lock()
@@ -154,6 +164,13 @@ def get_plan(H, W, J, L=8, max_order=2, device=None):
             p = Plan(H, W, J, L, max_order, dev)
             _PLAN_CACHE[key] = p
         return p
+
+
+def fma_peak_tflops(device=0):
+    """Measured fp32 FMA peak of the device (TFLOP/s)."""
+    t = ctypes.c_double()
+    _lib.check(_lib.load().wst2d_fma_peak(int(device), ctypes.byref(t)))
+    return t.value
 
 
 # ----------------------------------------------------------------------------- layouts

@@ -222,6 +222,10 @@ struct wst2d_plan {
     PlanTables pt{};
     float* d_tables = nullptr;
     std::vector<float> psi_hat, phi_hat;   // host copies (debug export)
+    // optional per-kernel timing (wst2d_profile): event pairs recorded around each launch
+    mutable std::mutex prof_mu;
+    mutable bool profiling = false;
+    mutable std::vector<cudaEvent_t> prof_cascade, prof_pool;   // (start, stop) pairs
 };
 
 namespace {
@@ -272,11 +276,38 @@ int build_filter_bank_gpu(wst2d_plan* p) {
     return WST2D_OK;
 }
 
-// signals per launch when the maps go to an internal scratch (bounded to ~1 GiB)
-long long chunk_signals(const wst2d_plan* p) {
+void prof_mark(const wst2d_plan* p, std::vector<cudaEvent_t>& v, cudaStream_t st) {
+    if (!p->profiling) return;
+    std::lock_guard<std::mutex> lk(p->prof_mu);
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) == cudaSuccess) { cudaEventRecord(e, st); v.push_back(e); }
+}
+
+// peak-rate probe for the roofline denominator: 8 independent FMA chains per thread
+__global__ void fma_peak_kernel(float* out, int iters) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
+    float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float b = 0.999f, c = 1e-3f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
+            a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// Signals per cascade launch when the maps go to the internal scratch: the scratch is bounded to
+// ~1 GiB, and the chunks are balanced and rounded to whole persistent-grid waves.
+long long chunk_signals(const wst2d_plan* p, long long nsig) {
     size_t map_bytes = (size_t)p->K * p->hout * p->hout * sizeof(float);
-    long long c = (long long)((size_t)1 << 30) / (long long)map_bytes;
-    if (c < p->grid_max) c = p->grid_max;
+    long long cmax = (long long)((size_t)1 << 30) / (long long)map_bytes;
+    if (cmax < p->grid_max) cmax = p->grid_max;
+    if (nsig <= cmax) return nsig;
+    long long nch = (nsig + cmax - 1) / cmax;
+    long long c = (nsig + nch - 1) / nch;
+    c = (c + p->grid_max - 1) / p->grid_max * p->grid_max;
     return c;
 }
 
@@ -286,7 +317,7 @@ int forward_impl(const wst2d_plan* p, const float* x_dev, long long nsig, float*
     const size_t sig_elems = (size_t)p->H * p->W;
     const size_t map_elems = (size_t)p->K * p->hout * p->hout;
     const size_t u0h_elems = (size_t)p->N * (p->N / 2 + 1);
-    const long long chunk = maps_dev ? nsig : (nsig < chunk_signals(p) ? nsig : chunk_signals(p));
+    const long long chunk = maps_dev ? nsig : chunk_signals(p, nsig);
     const int grid_all = (int)(nsig < p->grid_max ? nsig : p->grid_max);
     cfloat* d_u0h = nullptr; float* d_maps = nullptr;
     CUDA_TRY(cudaMallocAsync(&d_u0h, (size_t)grid_all * u0h_elems * sizeof(cfloat), st));
@@ -299,14 +330,18 @@ int forward_impl(const wst2d_plan* p, const float* x_dev, long long nsig, float*
         long long n = nsig - s0 < chunk ? nsig - s0 : chunk;
         int grid = (int)(n < p->grid_max ? n : p->grid_max);
         float* maps = maps_dev ? maps_dev + (size_t)s0 * map_elems : d_maps;
+        prof_mark(p, p->prof_cascade, st);
         cudaError_t e = p->ops->launch(p->pt, x_dev + (size_t)s0 * sig_elems, n, d_u0h, maps, grid, st);
+        prof_mark(p, p->prof_cascade, st);
         if (e != cudaSuccess) { rc = fail(WST2D_ERR_CUDA, std::string("cascade launch: ") + cudaGetErrorString(e)); break; }
         if (feats_dev) {
             long long nmaps = n * p->K;
             long long blocks = (nmaps + 7) / 8;                 // 8 warps per block
             if (blocks > 148 * 16) blocks = 148 * 16;
+            prof_mark(p, p->prof_pool, st);
             pool_kernel<<<(unsigned)blocks, 256, 0, st>>>(maps, feats_dev + (size_t)s0 * 2 * p->K, n, p->K,
                                                           p->hout * p->hout);
+            prof_mark(p, p->prof_pool, st);
             e = cudaGetLastError();
             if (e != cudaSuccess) { rc = fail(WST2D_ERR_CUDA, std::string("pool launch: ") + cudaGetErrorString(e)); break; }
         }
@@ -483,11 +518,69 @@ int wst2d_plan_filters(const wst2d_plan* p, float* psi_hat, float* phi_hat) {
     return WST2D_OK;
 }
 
+int wst2d_profile(wst2d_plan* p, int enable) {
+    if (!p) return fail(WST2D_ERR_ARG, "plan is NULL");
+    std::lock_guard<std::mutex> lk(p->prof_mu);
+    p->profiling = enable != 0;
+    return WST2D_OK;
+}
+
+int wst2d_profile_read(wst2d_plan* p, double* cascade_ms, double* pool_ms, int* cascade_launches) {
+    if (!p) return fail(WST2D_ERR_ARG, "plan is NULL");
+    DeviceGuard guard(p->device);
+    CUDA_TRY(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(p->prof_mu);
+    auto drain = [](std::vector<cudaEvent_t>& v, double& ms, int& n) {
+        ms = 0.0; n = 0;
+        for (size_t i = 0; i + 1 < v.size(); i += 2) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, v[i], v[i + 1]) == cudaSuccess) { ms += t; ++n; }
+        }
+        for (cudaEvent_t e : v) cudaEventDestroy(e);
+        v.clear();
+    };
+    double cm, pm; int cn, pn;
+    drain(p->prof_cascade, cm, cn);
+    drain(p->prof_pool, pm, pn);
+    if (cascade_ms) *cascade_ms = cm;
+    if (pool_ms) *pool_ms = pm;
+    if (cascade_launches) *cascade_launches = cn;
+    return WST2D_OK;
+}
+
+int wst2d_fma_peak(int device, double* tflops) {
+    if (!tflops) return fail(WST2D_ERR_ARG, "tflops is NULL");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail(WST2D_ERR_CUDA, "no such CUDA device");
+    DeviceGuard guard(device);
+    int sms = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int blocks = sms * 8, threads = 256, iters = 4096;
+    float* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, (size_t)blocks * threads * sizeof(float)));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        fma_peak_kernel<<<blocks, threads>>>(d, iters);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) break;
+        float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+        double fl = 2.0 * 128.0 * iters * (double)blocks * threads;   // 128 FMAs per iteration per thread
+        if (rep > 0 && fl / (ms * 1e-3) / 1e12 > best) best = fl / (ms * 1e-3) / 1e12;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    CUDA_TRY(cudaGetLastError());
+    *tflops = best;
+    return WST2D_OK;
+}
+
 int wst2d_launch_count(const wst2d_plan* p, int64_t B, int C) {
     if (!p) return fail(WST2D_ERR_ARG, "plan is NULL");
     long long nsig = (long long)B * C;
     if (nsig <= 0) return 0;
-    long long chunk = chunk_signals(p);
+    long long chunk = chunk_signals(p, nsig);
     long long nch = (nsig + chunk - 1) / chunk;
     return (int)(2 * nch);   // cascade + pool per chunk
 }
