@@ -81,6 +81,12 @@ int wst2d_launch_count(const wst2d_plan* plan, int64_t B, int C);
 int wst2d_profile(wst2d_plan* plan, int enable);
 int wst2d_profile_read(wst2d_plan* plan, double* cascade_ms, double* pool_ms, int* cascade_launches);
 
+/* Debug: run the cascade over nsig signals with a cycle-counting executor and return, per phase tag
+ * (csrc/wst_cascade.h PhaseKind * 8 + level; ntags must equal the library's tag count, 128), the SM
+ * cycles CTA 0 spent in that phase.  Synchronous.  Used by tools/phase_profile.py. */
+int wst2d_debug_phase_cycles(const wst2d_plan* plan, const float* x_dev, int64_t nsig, int64_t* cycles_host,
+                             int ntags);
+
 /* Measured fp32 FMA rate of `device` in TFLOP/s (dependent-chain-free FMA loop on all SMs): the
  * denominator of the compute roofline, which MEASURED_PEAKS.json does not carry. */
 int wst2d_fma_peak(int device, double* tflops);

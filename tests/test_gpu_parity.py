@@ -192,8 +192,9 @@ def test_u8_ingest_equals_float_path(wst):
     u8 = torch.randint(0, 256, (3, 32, 32, 3), dtype=torch.uint8, device="cuda")
     plan = wst.get_plan(32, 32, 2, 8)
     fu, _ = plan.forward(u8)
-    xf = (u8.permute(0, 3, 1, 2).float() / 255.0).contiguous()
-    ff, _ = plan.forward(xf)
+    # load_rgb_image semantics (train_and_save_model.py:54-55): IEEE float32 division, then HWC -> CHW
+    xf = np.ascontiguousarray(np.transpose(u8.cpu().numpy().astype(np.float32) / 255.0, (0, 3, 1, 2)))
+    ff, _ = plan.forward(torch.from_numpy(xf).cuda())
     assert torch.equal(fu, ff)
 
 

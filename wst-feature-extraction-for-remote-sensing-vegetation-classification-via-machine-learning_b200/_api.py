@@ -97,6 +97,9 @@ class Plan:
             if x.dtype != torch.float32:
                 raise TypeError("Input tensor must be float32 (or uint8 HWC).")
             B, C = x.shape[0], x.shape[1]
+        if B == 0:
+            return (torch.empty((0, C, 2, self.K), dtype=torch.float32, device=x.device) if want_features else None,
+                    torch.empty((0, C, self.K, self.h, self.w), dtype=torch.float32, device=x.device) if want_maps else None)
         feats = torch.empty((B, C, 2, self.K), dtype=torch.float32, device=x.device) if want_features else None
         maps = torch.empty((B, C, self.K, self.h, self.w), dtype=torch.float32, device=x.device) if want_maps else None
         stream = torch.cuda.current_stream(x.device).cuda_stream
@@ -136,6 +139,15 @@ class Plan:
 
     def launch_count(self, B, C):
         return int(_lib.load().wst2d_launch_count(self._h, B, C))
+
+    def phase_cycles(self, x):
+        """Debug: {(phase kind, level): SM cycles of CTA 0} for one cascade launch over x [B, C, H, W]."""
+        self._check_x(x)
+        arr = (ctypes.c_int64 * 128)()
+        _lib.check(_lib.load().wst2d_debug_phase_cycles(self._h, x.data_ptr(), x.shape[0] * x.shape[1], arr, 128))
+        kinds = ["twiddle", "input", "lp1", "lp2", "rfft_row_s", "rfft_row_c", "rfft_split", "rfft_col_s",
+                 "rfft_col_c", "u0_store", "prod1", "prod2", "ifft_col_c", "ifft_col_s", "ifft_row_c", "ifft_final"]
+        return {(kinds[i // 8], i % 8): int(arr[i]) for i in range(128) if arr[i]}
 
     def profile(self, enable=True):
         _lib.check(_lib.load().wst2d_profile(self._h, 1 if enable else 0))

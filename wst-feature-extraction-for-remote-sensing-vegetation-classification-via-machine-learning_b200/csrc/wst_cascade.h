@@ -28,7 +28,7 @@
 //     digit-swapped order pi(k) = (k % R1)*R2 + k / R1; forward = natural->swapped (DIF),
 //     inverse = swapped->natural (DIT), so no pass needs a reorder or a second barrier.
 //
-// The code is written as a sequence of barrier-separated phases `ex.phase([&](int tid){...})`.
+// The code is written as a sequence of barrier-separated phases `ex.template phase<TAG>([&](int tid){...})`.
 // On the GPU a phase is the lambda + __syncthreads(); in tests/emu the same phases are replayed
 // thread by thread on the CPU to check the index arithmetic against the oracle.
 #pragma once
@@ -142,13 +142,30 @@ struct PlanTables {
 };
 
 // ------------------------------------------------------------------ executors
+// Phase tags (kind * 8 + level of the array side being processed) — only used by the cycle-profiling
+// executor of the debug entry point; the production executor ignores them.
+enum PhaseKind { PK_TWIDDLE = 0, PK_INPUT, PK_LP1, PK_LP2, PK_RFFT_ROW_S, PK_RFFT_ROW_C, PK_RFFT_SPLIT,
+                 PK_RFFT_COL_S, PK_RFFT_COL_C, PK_U0_STORE, PK_PROD1, PK_PROD2, PK_IFFT_COL_C, PK_IFFT_COL_S,
+                 PK_IFFT_ROW_C, PK_IFFT_FINAL, PK_COUNT };
+constexpr int kNumPhaseTags = PK_COUNT * 8;
+
 #ifdef __CUDACC__
 struct DevExec {
-    template <class F> WST_D void phase(F&& f) { f((int)threadIdx.x); __syncthreads(); }
+    template <int TAG, class F> WST_D void phase(F&& f) { f((int)threadIdx.x); __syncthreads(); }
+};
+// Accumulates, per tag, the cycles from phase entry to barrier release as seen by thread 0.
+struct ProfExec {
+    long long* acc;    // shared memory, kNumPhaseTags entries
+    template <int TAG, class F> WST_D void phase(F&& f) {
+        long long t0 = clock64();
+        f((int)threadIdx.x);
+        __syncthreads();
+        if (threadIdx.x == 0) acc[TAG] += clock64() - t0;
+    }
 };
 #endif
 template <int NT> struct HostExec {
-    template <class F> void phase(F&& f) { for (int t = 0; t < NT; ++t) f(t); }
+    template <int TAG, class F> void phase(F&& f) { for (int t = 0; t < NT; ++t) f(t); }
 };
 
 // ------------------------------------------------------------------ FFT passes over shared memory
@@ -205,20 +222,20 @@ WST_D void pass_contig(int tid, cfloat* base, int narr, int AS, const cfloat* tw
 }
 
 // forward 1-D transforms of all lines: natural -> digit-swapped
-template <int M, int NL, int LS, int ES, int NT, class Exec>
+template <int M, int NL, int LS, int ES, int NT, int TAG_S, int TAG_C, class Exec>
 WST_D void fft_lines_fwd(Exec& ex, cfloat* base, int narr, int AS, const cfloat* tw) {
     if constexpr (Fft1<M>::R1 > 1) {
-        ex.phase([&](int tid) { pass_strided<M, -1, true, NL, LS, ES, NT>(tid, base, narr, AS, tw); });
+        ex.template phase<TAG_S>([&](int tid) { pass_strided<M, -1, true, NL, LS, ES, NT>(tid, base, narr, AS, tw); });
     }
-    ex.phase([&](int tid) { pass_contig<M, -1, false, NL, LS, ES, NT>(tid, base, narr, AS, tw); });
+    ex.template phase<TAG_C>([&](int tid) { pass_contig<M, -1, false, NL, LS, ES, NT>(tid, base, narr, AS, tw); });
 }
 
 // inverse 1-D transforms of all lines: digit-swapped -> natural (unnormalised)
-template <int M, int NL, int LS, int ES, int NT, class Exec>
+template <int M, int NL, int LS, int ES, int NT, int TAG_C, int TAG_S, class Exec>
 WST_D void fft_lines_inv(Exec& ex, cfloat* base, int narr, int AS, const cfloat* tw) {
-    ex.phase([&](int tid) { pass_contig<M, +1, true, NL, LS, ES, NT>(tid, base, narr, AS, tw); });
+    ex.template phase<TAG_C>([&](int tid) { pass_contig<M, +1, true, NL, LS, ES, NT>(tid, base, narr, AS, tw); });
     if constexpr (Fft1<M>::R1 > 1) {
-        ex.phase([&](int tid) { pass_strided<M, +1, false, NL, LS, ES, NT>(tid, base, narr, AS, tw); });
+        ex.template phase<TAG_S>([&](int tid) { pass_strided<M, +1, false, NL, LS, ES, NT>(tid, base, narr, AS, tw); });
     }
 }
 
@@ -262,25 +279,25 @@ WST_D void pass_rows_final_modulus(int tid, cfloat* base, int narr, int AS, cons
 }
 
 // Inverse 2-D FFT of narr digit-swapped M x M spectra (pitch M+1) + modulus + row pairing.
-template <int M, int NT, class Exec>
+template <int M, int NT, int LV, class Exec>
 WST_D void ifft2_modulus_pair(Exec& ex, cfloat* base, int narr, const cfloat* tw) {
     constexpr int P = M + 1, AS = M * (M + 1);
-    fft_lines_inv<M, M, 1, P, NT>(ex, base, narr, AS, tw);              // columns (along rows index)
+    fft_lines_inv<M, M, 1, P, NT, PK_IFFT_COL_C * 8 + LV, PK_IFFT_COL_S * 8 + LV>(ex, base, narr, AS, tw);   // columns
     if constexpr (Fft1<M>::R1 > 1) {
-        ex.phase([&](int tid) { pass_contig<M, +1, true, M, P, 1, NT>(tid, base, narr, AS, tw); });
+        ex.template phase<PK_IFFT_ROW_C * 8 + LV>([&](int tid) { pass_contig<M, +1, true, M, P, 1, NT>(tid, base, narr, AS, tw); });
     }
-    ex.phase([&](int tid) { pass_rows_final_modulus<M, NT>(tid, base, narr, AS, tw); });
+    ex.template phase<PK_IFFT_FINAL * 8 + LV>([&](int tid) { pass_rows_final_modulus<M, NT>(tid, base, narr, AS, tw); });
 }
 
 // Real 2-D forward FFT of narr paired-row arrays z (stride ZS, pitch M+1, M/2 rows) into
 // half spectra U^[pi(k)][l], l = 0..M/2 (stride UHS = M*(M/2+1), pitch M/2+1).
-template <int M, int NT, class Exec>
+template <int M, int NT, int LV, class Exec>
 WST_D void rfft2_from_pairs(Exec& ex, cfloat* z, int ZS, cfloat* uh, int narr, const cfloat* tw) {
     constexpr int P = M + 1, HALF = M / 2, PH = M / 2 + 1, UHS = M * PH;
     // rows of z (along y): natural -> swapped
-    fft_lines_fwd<M, HALF, P, 1, NT>(ex, z, narr, ZS, tw);
+    fft_lines_fwd<M, HALF, P, 1, NT, PK_RFFT_ROW_S * 8 + LV, PK_RFFT_ROW_C * 8 + LV>(ex, z, narr, ZS, tw);
     // split the packed rows:  A = FFT(row x), B = FFT(row x + M/2)
-    ex.phase([&](int tid) {
+    ex.template phase<PK_RFFT_SPLIT * 8 + LV>([&](int tid) {
         const int total = narr * PH * HALF;
         for (int b = tid; b < total; b += NT) {
             int x = b % HALF, r = b / HALF;
@@ -296,7 +313,7 @@ WST_D void rfft2_from_pairs(Exec& ex, cfloat* z, int ZS, cfloat* uh, int narr, c
         }
     });
     // columns of U^ (along rows index): natural -> swapped
-    fft_lines_fwd<M, PH, 1, PH, NT>(ex, uh, narr, UHS, tw);
+    fft_lines_fwd<M, PH, 1, PH, NT, PK_RFFT_COL_S * 8 + LV, PK_RFFT_COL_C * 8 + LV>(ex, uh, narr, UHS, tw);
 }
 
 // Hermitian lookup U(k, l) from a half spectrum stored as [pi(k)][l], l <= M/2.
@@ -360,7 +377,7 @@ WST_D void product_fold(int tid, const cfloat* uh, const float* filt, cfloat* ou
 //   S[i][i'] = sum_{x,y} Gr[x][i] * U[x][y] * Gc[y][i'],  i, i' < HOUT
 // written to maps + coef(g)*HOUT*HOUT for arrays with coef(g) >= 0.
 // Scratch: the dead second half of each array (rows >= M/2).
-template <int M, int HOUT, int HP, int NT, class Exec, class CoefFn>
+template <int M, int HOUT, int HP, int NT, int LV, class Exec, class CoefFn>
 WST_D void lowpass_maps(Exec& ex, cfloat* z, int ZS, int narr, const float* gr, const float* gc,
                         float* maps, CoefFn coef) {
     constexpr int P = M + 1, HALF = M / 2;
@@ -369,7 +386,7 @@ WST_D void lowpass_maps(Exec& ex, cfloat* z, int ZS, int narr, const float* gr, 
     const int want = (NT + narr * M - 1) / (narr * M);
     const int nch = want < 1 ? 1 : (want > NCH_FIT ? NCH_FIT : (want > HALF ? HALF : want));
     const int xper = (HALF + nch - 1) / nch;
-    ex.phase([&](int tid) {
+    ex.template phase<PK_LP1 * 8 + LV>([&](int tid) {
         const int total = narr * nch * M;
         for (int b = tid; b < total; b += NT) {
             int y = b % M, r = b / M;
@@ -396,7 +413,7 @@ WST_D void lowpass_maps(Exec& ex, cfloat* z, int ZS, int narr, const float* gr, 
             static_for<0, HOUT>([&](auto I) { tp[decltype(I)::value * M] = acc[decltype(I)::value]; });
         }
     });
-    ex.phase([&](int tid) {
+    ex.template phase<PK_LP2 * 8 + LV>([&](int tid) {
         const int total = narr * HOUT * HOUT;
         for (int b = tid; b < total; b += NT) {
             int ic = b % HOUT, r = b / HOUT;
@@ -438,7 +455,7 @@ struct Cascade {
 
     // once per CTA
     WST_D void load_twiddles() {
-        ex.phase([&](int tid) {
+        ex.template phase<PK_TWIDDLE * 8>([&](int tid) {
             static_for<0, J>([&](auto Jj) {
                 constexpr int j = decltype(Jj)::value;
                 constexpr int m = C::msize(j);
@@ -451,7 +468,7 @@ struct Cascade {
     WST_D void input_stage(const float* x) {
         constexpr int P = N + 1, HALF = N / 2, PH = N / 2 + 1;
         const int H = pt.H, W = pt.W, pt_top = pt.pad_top, pt_left = pt.pad_left;
-        ex.phase([&](int tid) {
+        ex.template phase<PK_INPUT * 8>([&](int tid) {
             for (int o = tid; o < HALF * N; o += NT) {
                 int c = o % N, r = o / N;
                 int sc = c - pt_left; sc = sc < 0 ? -sc : (sc >= W ? 2 * (W - 1) - sc : sc);
@@ -460,10 +477,10 @@ struct Cascade {
                 sm[r * P + c] = cmake(x[r0 * W + sc], x[r1 * W + sc]);
             }
         });
-        lowpass_maps<N, HOUT, HP, NT>(ex, sm, 0, 1, pt.gr[0], pt.gc[0], maps, [](int) { return 0; });
+        lowpass_maps<N, HOUT, HP, NT, 0>(ex, sm, 0, 1, pt.gr[0], pt.gc[0], maps, [](int) { return 0; });
         cfloat* uh = sm + C::OFFB(0);
-        rfft2_from_pairs<N, NT>(ex, sm, 0, uh, 1, tw(0));
-        ex.phase([&](int tid) {
+        rfft2_from_pairs<N, NT, 0>(ex, sm, 0, uh, 1, tw(0));
+        ex.template phase<PK_U0_STORE * 8>([&](int tid) {
             for (int o = tid; o < N * PH; o += NT) u0h[o] = uh[o];
         });
     }
@@ -476,9 +493,9 @@ struct Cascade {
         const int cbase = order2_base(J1, t1) + (J2 - J1 - 1) * L;
         for (int grp = 0; grp < ngroups; ++grp) {
             const float* filt = pt.psi2[J2][J1] + (size_t)grp * MP * MP * G;
-            ex.phase([&](int tid) { product_fold<MP, MC, G, NT>(tid, uh_parent, filt, sm); });
-            ifft2_modulus_pair<MC, NT>(ex, sm, G, tw(J2));
-            lowpass_maps<MC, HOUT, HP, NT>(ex, sm, C::vsz(MC), G, pt.gr[J2], pt.gc[J2], maps,
+            ex.template phase<PK_PROD2 * 8 + J2>([&](int tid) { product_fold<MP, MC, G, NT>(tid, uh_parent, filt, sm); });
+            ifft2_modulus_pair<MC, NT, J2>(ex, sm, G, tw(J2));
+            lowpass_maps<MC, HOUT, HP, NT, J2>(ex, sm, C::vsz(MC), G, pt.gr[J2], pt.gc[J2], maps,
                                            [&](int g) { int t2 = grp * G + g; return t2 < L ? cbase + t2 : -1; });
         }
     }
@@ -490,14 +507,14 @@ struct Cascade {
         const int ngroups = (L + GPn - 1) / GPn;
         for (int grp = 0; grp < ngroups; ++grp) {
             const float* filt = pt.psi1[J1] + (size_t)grp * N * N * GPn;
-            ex.phase([&](int tid) { product_fold<N, M, GPn, NT>(tid, u0h, filt, sm); });
-            ifft2_modulus_pair<M, NT>(ex, sm, GPn, tw(J1));
-            lowpass_maps<M, HOUT, HP, NT>(ex, sm, C::vsz(M), GPn, pt.gr[J1], pt.gc[J1], maps,
+            ex.template phase<PK_PROD1 * 8 + J1>([&](int tid) { product_fold<N, M, GPn, NT>(tid, u0h, filt, sm); });
+            ifft2_modulus_pair<M, NT, J1>(ex, sm, GPn, tw(J1));
+            lowpass_maps<M, HOUT, HP, NT, J1>(ex, sm, C::vsz(M), GPn, pt.gr[J1], pt.gc[J1], maps,
                                           [&](int g) { int t1 = grp * GPn + g; return t1 < L ? 1 + J1 * L + t1 : -1; });
             if constexpr (C::has_children(J1)) {
                 if (pt.max_order >= 2) {
                     cfloat* uh = sm + C::OFFB(J1);
-                    rfft2_from_pairs<M, NT>(ex, sm, C::vsz(M), uh, GPn, tw(J1));
+                    rfft2_from_pairs<M, NT, J1>(ex, sm, C::vsz(M), uh, GPn, tw(J1));
                     for (int g = 0; g < GPn; ++g) {
                         int t1 = grp * GPn + g;
                         if (t1 >= L) break;

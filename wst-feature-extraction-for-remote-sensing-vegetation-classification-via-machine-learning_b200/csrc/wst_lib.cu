@@ -59,6 +59,32 @@ cascade_kernel(const PlanTables pt, const float* __restrict__ x, long long nsig,
     }
 }
 
+// Debug twin of cascade_kernel: same program, executor that accumulates clock64() per phase tag.
+// CTA 0's totals (over the signals it processed) are written to `cycles`.
+template <class C>
+__global__ void __launch_bounds__(C::NT, 1)
+cascade_prof_kernel(const PlanTables pt, const float* __restrict__ x, long long nsig, cfloat* u0h_scratch,
+                    float* maps, long long* cycles) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ long long acc[kNumPhaseTags];
+    cfloat* sm = reinterpret_cast<cfloat*>(smem_raw);
+    cfloat* twsm = sm + C::smem_cfloats();
+    for (int i = threadIdx.x; i < kNumPhaseTags; i += C::NT) acc[i] = 0;
+    __syncthreads();
+    ProfExec ex{acc};
+    const size_t sig_elems = (size_t)pt.H * pt.W;
+    const size_t map_elems = (size_t)pt.K * C::HOUT * C::HOUT;
+    Cascade<C, ProfExec> prog{ex, pt, sm, twsm,
+                              u0h_scratch + (size_t)blockIdx.x * (C::N * (C::N / 2 + 1)), nullptr};
+    prog.load_twiddles();
+    for (long long s = blockIdx.x; s < nsig; s += gridDim.x) {
+        prog.maps = maps + (size_t)s * map_elems;
+        prog.run(x + (size_t)s * sig_elems);
+    }
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i < kNumPhaseTags; i += C::NT) cycles[i] = acc[i];
+}
+
 // ------------------------------------------------------------------------------------------------
 // pooling: one warp per coefficient map
 // ------------------------------------------------------------------------------------------------
@@ -178,12 +204,23 @@ struct CfgOps {
     bool (*build)(int, const float*, const float*, std::vector<float>&, TableOffsets&, std::string&);
     void (*bind)(PlanTables&, const float*, const TableOffsets&);
     cudaError_t (*launch)(const PlanTables&, const float*, long long, cfloat*, float*, int, cudaStream_t);
+    cudaError_t (*launch_prof)(const PlanTables&, const float*, long long, cfloat*, float*, long long*, int, cudaStream_t);
 };
 
 template <class C>
 cudaError_t launch_cascade(const PlanTables& pt, const float* x, long long nsig, cfloat* u0h, float* maps,
                            int grid, cudaStream_t st) {
     cascade_kernel<C><<<grid, C::NT, C::smem_bytes(), st>>>(pt, x, nsig, u0h, maps);
+    return cudaGetLastError();
+}
+
+template <class C>
+cudaError_t launch_cascade_prof(const PlanTables& pt, const float* x, long long nsig, cfloat* u0h, float* maps,
+                                long long* cycles, int grid, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(cascade_prof_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)C::smem_bytes());
+    if (e != cudaSuccess) return e;
+    cascade_prof_kernel<C><<<grid, C::NT, C::smem_bytes(), st>>>(pt, x, nsig, u0h, maps, cycles);
     return cudaGetLastError();
 }
 
@@ -196,6 +233,7 @@ CfgOps make_ops() {
     o.build = &build_tables<C>;
     o.bind = &bind_tables<C>;
     o.launch = &launch_cascade<C>;
+    o.launch_prof = &launch_cascade_prof<C>;
     return o;
 }
 
@@ -436,7 +474,8 @@ int wst2d_forward(const wst2d_plan* p, const float* x_dev, int64_t B, int C, flo
                   float* maps_dev, void* cuda_stream) {
     if (!p) return fail(WST2D_ERR_ARG, "plan is NULL");
     if (B < 0 || C < 1) return fail(WST2D_ERR_ARG, "B must be >= 0 and C >= 1");
-    if (B > 0 && !x_dev) return fail(WST2D_ERR_ARG, "x_dev is NULL");
+    if (B == 0) return WST2D_OK;
+    if (!x_dev) return fail(WST2D_ERR_ARG, "x_dev is NULL");
     if (!feats_dev && !maps_dev) return fail(WST2D_ERR_ARG, "both outputs are NULL");
     DeviceGuard guard(p->device);
     return forward_impl(p, x_dev, (long long)B * C, feats_dev, maps_dev, (cudaStream_t)cuda_stream);
@@ -446,9 +485,9 @@ int wst2d_forward_u8(const wst2d_plan* p, const uint8_t* x_dev, int64_t B, int C
                      float* maps_dev, void* cuda_stream) {
     if (!p) return fail(WST2D_ERR_ARG, "plan is NULL");
     if (B < 0 || C < 1) return fail(WST2D_ERR_ARG, "B must be >= 0 and C >= 1");
-    if (B > 0 && !x_dev) return fail(WST2D_ERR_ARG, "x_dev is NULL");
-    if (!feats_dev && !maps_dev) return fail(WST2D_ERR_ARG, "both outputs are NULL");
     if (B == 0) return WST2D_OK;
+    if (!x_dev) return fail(WST2D_ERR_ARG, "x_dev is NULL");
+    if (!feats_dev && !maps_dev) return fail(WST2D_ERR_ARG, "both outputs are NULL");
     DeviceGuard guard(p->device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const size_t n = (size_t)B * C * p->H * p->W;
@@ -573,6 +612,25 @@ int wst2d_fma_peak(int device, double* tflops) {
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
     CUDA_TRY(cudaGetLastError());
     *tflops = best;
+    return WST2D_OK;
+}
+
+int wst2d_debug_phase_cycles(const wst2d_plan* p, const float* x_dev, int64_t nsig, int64_t* cycles_host,
+                             int ntags) {
+    if (!p || !x_dev || !cycles_host) return fail(WST2D_ERR_ARG, "NULL argument");
+    if (ntags != kNumPhaseTags) return fail(WST2D_ERR_ARG, "ntags must be " + std::to_string(kNumPhaseTags));
+    if (nsig <= 0) return fail(WST2D_ERR_ARG, "nsig must be positive");
+    DeviceGuard guard(p->device);
+    const int grid = (int)(nsig < p->grid_max ? nsig : p->grid_max);
+    cfloat* d_u0h = nullptr; float* d_maps = nullptr; long long* d_cyc = nullptr;
+    CUDA_TRY(cudaMalloc(&d_u0h, (size_t)grid * p->N * (p->N / 2 + 1) * sizeof(cfloat)));
+    CUDA_TRY(cudaMalloc(&d_maps, (size_t)nsig * p->K * p->hout * p->hout * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&d_cyc, kNumPhaseTags * sizeof(long long)));
+    cudaError_t e = p->ops->launch_prof(p->pt, x_dev, nsig, d_u0h, d_maps, d_cyc, grid, nullptr);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(cycles_host, d_cyc, kNumPhaseTags * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(d_u0h); cudaFree(d_maps); cudaFree(d_cyc);
+    if (e != cudaSuccess) return fail(WST2D_ERR_CUDA, std::string("phase profile: ") + cudaGetErrorString(e));
     return WST2D_OK;
 }
 
