@@ -143,11 +143,13 @@ class Plan:
     def phase_cycles(self, x):
         """Debug: {(phase kind, level): SM cycles of CTA 0} for one cascade launch over x [B, C, H, W]."""
         self._check_x(x)
-        arr = (ctypes.c_int64 * 128)()
-        _lib.check(_lib.load().wst2d_debug_phase_cycles(self._h, x.data_ptr(), x.shape[0] * x.shape[1], arr, 128))
         kinds = ["twiddle", "input", "lp1", "lp2", "rfft_row_s", "rfft_row_c", "rfft_split", "rfft_col_s",
-                 "rfft_col_c", "u0_store", "prod1", "prod2", "ifft_col_c", "ifft_col_s", "ifft_row_c", "ifft_final"]
-        return {(kinds[i // 8], i % 8): int(arr[i]) for i in range(128) if arr[i]}
+                 "rfft_col_c", "u0_store", "prod1", "prod2", "ifft_col_c", "ifft_col_s", "ifft_row_c", "ifft_final",
+                 "lp_reduce", "lp_store"]
+        n = 8 * len(kinds)
+        arr = (ctypes.c_int64 * n)()
+        _lib.check(_lib.load().wst2d_debug_phase_cycles(self._h, x.data_ptr(), x.shape[0] * x.shape[1], arr, n))
+        return {(kinds[i // 8], i % 8): int(arr[i]) for i in range(n) if arr[i]}
 
     def profile(self, enable=True):
         _lib.check(_lib.load().wst2d_profile(self._h, 1 if enable else 0))

@@ -37,6 +37,9 @@
 namespace wst {
 
 constexpr int kMaxJ = 6;
+constexpr int kMaxL = 8;                 // orientations per scale supported by the compiled cascades
+constexpr int kMaxPairs = kMaxJ * (kMaxJ - 1) / 2;
+WST_CX int pair_index(int j2, int j1) { return j2 * (j2 - 1) / 2 + j1; }
 constexpr int kSmemCfloats = 27000;      // data region budget (216,000 B) of the 227 KB a CTA may use
 
 // ------------------------------------------------------------------ 1-D factorisation n = R1*R2
@@ -125,8 +128,27 @@ struct Cfg {
         for (int i = 0; i < j; ++i) o += msize(i);
         return o;
     }
-    static constexpr int tw_total = 2 * N;      // sum_j N>>j < 2N
-    static WST_CX size_t smem_bytes() { return (size_t)(smem_cfloats() + tw_total) * sizeof(cfloat); }
+    static WST_CX int tw_sum() { int o = 0; for (int i = 0; i < J; ++i) o += msize(i); return o; }
+    static constexpr int tw_total = (2 * N - (N >> (J - 1)) + 7) & ~7;   // sum_j N>>j, padded to 8
+    // low-pass operator tables G[j][m_j][HP] (floats), one per level, resident in shared memory
+    static WST_CX int g_offset(int j) { return tw_offset(j) * HP; }
+    static constexpr int g_total = tw_total * HP;
+    // The low-pass of an array can be fused into the last pass of its inverse FFT when the 2*HOUT
+    // partial sums of a thread fit in the shared-memory slots that thread owns (see pass_rows_final).
+    static WST_CX bool lp_fused(int m, bool write_z) {
+        int r1 = fft_R1(m);
+        if (r1 == 1) return !write_z;
+        return write_z ? (HOUT <= r1) : (HOUT / 2 <= r1);
+    }
+    static WST_CX bool any_fused() {
+        for (int j = 0; j < J; ++j) if (lp_fused(msize(j), has_children(j)) || (j > 0 && lp_fused(msize(j), false))) return true;
+        return false;
+    }
+    static constexpr int LP_SLOTS = 40;         // (array, row-chunk) partial maps held between the two reduce phases
+    static WST_CX int lpbuf_floats() { return any_fused() ? LP_SLOTS * HOUT * HOUT : 0; }
+    static WST_CX size_t smem_bytes() {
+        return (size_t)(smem_cfloats() + tw_total) * sizeof(cfloat) + (size_t)(g_total + lpbuf_floats()) * sizeof(float);
+    }
     static_assert(level_total(0, 1) <= kSmemCfloats, "padded size too large for the shared-memory cascade");
 };
 
@@ -137,16 +159,22 @@ struct PlanTables {
     const cfloat* tw[kMaxJ];               // tw[j][k1*R2+i2] = exp(-2 pi i * i2*k1 / m_j)
     const float* gr[kMaxJ];                // row   low-pass operator, [m_j][HP]  (x-major)
     const float* gc[kMaxJ];                // column low-pass operator, [m_j][HP]
-    const float* psi1[kMaxJ];              // order-1 filters of scale j at level 0: [ceil(L/GP)][N][N][GP]
-    const float* psi2[kMaxJ][kMaxJ];       // [j2][j1]: scale-j2 filters at level j1: [ceil(L/G)][m][m][G]
+    const float* psi1[kMaxJ];              // order-1 filters of scale j at level 0: [ceil(L/GP)][N][N][GP], GP = GP(j)
+    const float* psi2[kMaxJ][kMaxJ];       // [j2][j1]: scale j2 periodised to level j1: [ceil(L/G)][m][m][G], G = G2(j1, j2)
+    // Bounding box of the support of every theta-group of filters (entries above kSupportEps * max|psi^|):
+    // one cyclic row span and one cyclic column span, each packed lo << 16 | len.  They travel in the kernel parameter
+    // block (constant bank), so the product loops have no dependent global loads.
+    int bb1[kMaxJ][kMaxL][2];              // order-1: scale j at level 0
+    int bb2[kMaxPairs][kMaxL][2];          // order-2: pair_index(j2, j1): scale j2 at level j1
 };
+constexpr float kSupportEps = 1e-7f;
 
 // ------------------------------------------------------------------ executors
 // Phase tags (kind * 8 + level of the array side being processed) — only used by the cycle-profiling
 // executor of the debug entry point; the production executor ignores them.
 enum PhaseKind { PK_TWIDDLE = 0, PK_INPUT, PK_LP1, PK_LP2, PK_RFFT_ROW_S, PK_RFFT_ROW_C, PK_RFFT_SPLIT,
                  PK_RFFT_COL_S, PK_RFFT_COL_C, PK_U0_STORE, PK_PROD1, PK_PROD2, PK_IFFT_COL_C, PK_IFFT_COL_S,
-                 PK_IFFT_ROW_C, PK_IFFT_FINAL, PK_COUNT };
+                 PK_IFFT_ROW_C, PK_IFFT_FINAL, PK_LPR, PK_LPS, PK_COUNT };
 constexpr int kNumPhaseTags = PK_COUNT * 8;
 
 #ifdef __CUDACC__
@@ -239,54 +267,116 @@ WST_D void fft_lines_inv(Exec& ex, cfloat* base, int narr, int AS, const cfloat*
     }
 }
 
-// Last pass of the inverse row transform fused with modulus and row pairing:
-//   z[x][y] = ( |u[x][y]|, |u[x + M/2][y]| ),  x < M/2, written over row x of the same array.
-template <int M, int NT>
-WST_D void pass_rows_final_modulus(int tid, cfloat* base, int narr, int AS, const cfloat* tw) {
+// Last pass of the inverse row transform, fused with modulus, row pairing and (optionally) the first
+// half of the separable low-pass.
+//   WRITE_Z: z[x][y] = ( |u[x][y]|, |u[x + M/2][y]| ), x < M/2, written over row x (input of rfft2_from_pairs)
+//   LPF:     each thread contracts the |u| values it holds with Gc over y and parks the 2*HOUT partial sums
+//            in shared-memory slots it owns (they were its own inputs):
+//              no z :  row r, column slot (q*R2 + i2) <- (acc_r[2q], acc_r[2q+1]),  q < HOUT/2
+//              z    :  row x+M/2, slot (q*R2 + i2) <- acc_x[..],  slot ((HOUT/2+q)*R2 + i2) <- acc_{x+M/2}[..]
+//            (single-pass lengths hold whole rows: the slot is column q and the sum over y is complete).
+template <int M, int NT, bool WRITE_Z, bool LPF, int HOUT, int HP>
+WST_D void pass_rows_final(int tid, cfloat* base, int narr, int AS, const float* gc) {
     constexpr int R1 = Fft1<M>::R1, R2 = Fft1<M>::R2, P = M + 1, HALF = M / 2;
-    if constexpr (R1 > 1) {
-        const int total = narr * R2 * HALF;
-        for (int b = tid; b < total; b += NT) {
-            int x = b % HALF, r = b / HALF;
-            int i2 = r % R2, g = r / R2;
-            cfloat* p0 = base + g * AS + x * P + i2;
-            cfloat* p1 = p0 + HALF * P;
-            cfloat a[R1], c[R1];
-            static_for<0, R1>([&](auto K) { constexpr int k = decltype(K)::value; a[k] = p0[k * R2]; c[k] = p1[k * R2]; });
-            dft<R1, +1>(a);
-            dft<R1, +1>(c);
-            static_for<0, R1>([&](auto K) {
+    constexpr int NV = (R1 > 1) ? R1 : R2;            // values per row held by one thread
+    constexpr int YS = (R1 > 1) ? R2 : 1;             // their stride along y
+    const int nsub = (R1 > 1) ? R2 : 1;
+    const int total = narr * nsub * HALF;
+    for (int b = tid; b < total; b += NT) {
+        int x = b % HALF, r = b / HALF;
+        int i2 = r % nsub, g = r / nsub;
+        cfloat* p0 = base + g * AS + x * P + i2;
+        cfloat* p1 = p0 + HALF * P;
+        cfloat a[NV], c[NV];
+        static_for<0, NV>([&](auto K) { constexpr int k = decltype(K)::value; a[k] = p0[k * YS]; c[k] = p1[k * YS]; });
+        dft<NV, +1>(a);
+        dft<NV, +1>(c);
+        static_for<0, NV>([&](auto K) {
+            constexpr int k = decltype(K)::value;
+            a[k].x = cabs_(a[k]);
+            a[k].y = cabs_(c[k]);
+        });
+        if constexpr (LPF) {
+            float acc0[HOUT], acc1[HOUT];
+            static_for<0, HOUT>([&](auto I) { acc0[decltype(I)::value] = 0.f; acc1[decltype(I)::value] = 0.f; });
+            static_for<0, NV>([&](auto K) {
                 constexpr int k = decltype(K)::value;
-                p0[k * R2] = cmake(cabs_(a[k]), cabs_(c[k]));
+                const float* gy = gc + (k * YS + i2) * HP;
+                static_for<0, HP / 4>([&](auto Q) {
+                    constexpr int q = decltype(Q)::value;
+                    float4 w = *reinterpret_cast<const float4*>(gy + 4 * q);
+                    if constexpr (4 * q + 0 < HOUT) { acc0[4 * q + 0] += w.x * a[k].x; acc1[4 * q + 0] += w.x * a[k].y; }
+                    if constexpr (4 * q + 1 < HOUT) { acc0[4 * q + 1] += w.y * a[k].x; acc1[4 * q + 1] += w.y * a[k].y; }
+                    if constexpr (4 * q + 2 < HOUT) { acc0[4 * q + 2] += w.z * a[k].x; acc1[4 * q + 2] += w.z * a[k].y; }
+                    if constexpr (4 * q + 3 < HOUT) { acc0[4 * q + 3] += w.w * a[k].x; acc1[4 * q + 3] += w.w * a[k].y; }
+                });
             });
-        }
-    } else {   // single-pass length: the whole row transform happens here
-        const int total = narr * HALF;
-        for (int b = tid; b < total; b += NT) {
-            int x = b % HALF, g = b / HALF;
-            cfloat* p0 = base + g * AS + x * P;
-            cfloat* p1 = p0 + HALF * P;
-            cfloat a[R2], c[R2];
-            static_for<0, R2>([&](auto I) { constexpr int i = decltype(I)::value; a[i] = p0[i]; c[i] = p1[i]; });
-            dft<R2, +1>(a);
-            dft<R2, +1>(c);
-            static_for<0, R2>([&](auto I) {
-                constexpr int i = decltype(I)::value;
-                p0[i] = cmake(cabs_(a[i]), cabs_(c[i]));
-            });
+            if constexpr (WRITE_Z) {
+                static_for<0, NV>([&](auto K) { constexpr int k = decltype(K)::value; p0[k * YS] = a[k]; });
+                static_for<0, HOUT / 2>([&](auto Q) {
+                    constexpr int q = decltype(Q)::value;
+                    p1[q * YS] = cmake(acc0[2 * q], acc0[2 * q + 1]);
+                    p1[(HOUT / 2 + q) * YS] = cmake(acc1[2 * q], acc1[2 * q + 1]);
+                });
+            } else {
+                static_for<0, HOUT / 2>([&](auto Q) {
+                    constexpr int q = decltype(Q)::value;
+                    p0[q * YS] = cmake(acc0[2 * q], acc0[2 * q + 1]);
+                    p1[q * YS] = cmake(acc1[2 * q], acc1[2 * q + 1]);
+                });
+            }
+        } else {
+            static_for<0, NV>([&](auto K) { constexpr int k = decltype(K)::value; p0[k * YS] = a[k]; });
         }
     }
 }
 
-// Inverse 2-D FFT of narr digit-swapped M x M spectra (pitch M+1) + modulus + row pairing.
-template <int M, int NT, int LV, class Exec>
-WST_D void ifft2_modulus_pair(Exec& ex, cfloat* base, int narr, const cfloat* tw) {
-    constexpr int P = M + 1, AS = M * (M + 1);
-    fft_lines_inv<M, M, 1, P, NT, PK_IFFT_COL_C * 8 + LV, PK_IFFT_COL_S * 8 + LV>(ex, base, narr, AS, tw);   // columns
-    if constexpr (Fft1<M>::R1 > 1) {
-        ex.template phase<PK_IFFT_ROW_C * 8 + LV>([&](int tid) { pass_contig<M, +1, true, M, P, 1, NT>(tid, base, narr, AS, tw); });
-    }
-    ex.template phase<PK_IFFT_FINAL * 8 + LV>([&](int tid) { pass_rows_final_modulus<M, NT>(tid, base, narr, AS, tw); });
+// Second half of the fused low-pass: reduce the parked partial sums over the threads of a row, contract
+// with Gr over chunks of rows (phase LPR), then sum the chunks and store the map (phase LPS).
+template <int M, int NT, bool WRITE_Z, int HOUT, int HP, int LPSLOTS, int LV, class Exec, class CoefFn>
+WST_D void lowpass_reduce(Exec& ex, cfloat* base, int narr, int AS, const float* gr, float* lpbuf, float* maps,
+                          CoefFn coef) {
+    constexpr int R1 = Fft1<M>::R1, R2 = Fft1<M>::R2, P = M + 1, HALF = M / 2;
+    constexpr int NSUB = (R1 > 1) ? R2 : 1, YS = (R1 > 1) ? R2 : 1;
+    int nchunks = LPSLOTS / narr;
+    if (nchunks > (M + 7) / 8) nchunks = (M + 7) / 8;
+    if (nchunks < 1) nchunks = 1;
+    const int rc = (M + nchunks - 1) / nchunks;
+    ex.template phase<PK_LPR * 8 + LV>([&](int tid) {
+        const int total = narr * nchunks * HOUT;
+        for (int b = tid; b < total; b += NT) {
+            int ic = b % HOUT, r = b / HOUT;
+            int ch = r % nchunks, g = r / nchunks;
+            const float* fb = reinterpret_cast<const float*>(base + g * AS);
+            float acc[HOUT];
+            static_for<0, HOUT>([&](auto I) { acc[decltype(I)::value] = 0.f; });
+            int r0 = ch * rc, r1 = r0 + rc < M ? r0 + rc : M;
+            for (int row = r0; row < r1; ++row) {
+                int srow, scol;
+                if constexpr (WRITE_Z) { srow = row < HALF ? row + HALF : row; scol = (row < HALF ? 0 : HOUT / 2) + ic / 2; }
+                else { srow = row; scol = ic / 2; }
+                const float* sp = fb + (size_t)(srow * P + scol * YS) * 2 + (ic & 1);
+                float t = 0.f;
+                for (int i2 = 0; i2 < NSUB; ++i2) t += sp[2 * i2];
+                const float* gx = gr + row * HP;
+                static_for<0, HOUT>([&](auto I) { acc[decltype(I)::value] += gx[decltype(I)::value] * t; });
+            }
+            float* o = lpbuf + (size_t)(g * nchunks + ch) * HOUT * HOUT + ic;
+            static_for<0, HOUT>([&](auto I) { o[decltype(I)::value * HOUT] = acc[decltype(I)::value]; });
+        }
+    });
+    ex.template phase<PK_LPS * 8 + LV>([&](int tid) {
+        const int total = narr * HOUT * HOUT;
+        for (int b = tid; b < total; b += NT) {
+            int e = b % (HOUT * HOUT), g = b / (HOUT * HOUT);
+            int cidx = coef(g);
+            if (cidx < 0) continue;
+            const float* o = lpbuf + (size_t)g * nchunks * HOUT * HOUT + e;
+            float sacc = 0.f;
+            for (int ch = 0; ch < nchunks; ++ch) sacc += o[ch * HOUT * HOUT];
+            maps[(size_t)cidx * (HOUT * HOUT) + e] = sacc;
+        }
+    });
 }
 
 // Real 2-D forward FFT of narr paired-row arrays z (stride ZS, pitch M+1, M/2 rows) into
@@ -326,42 +416,80 @@ WST_D cfloat herm_get(const cfloat* uh, int k, int l) {
     return cmake(v.x, -v.y);
 }
 
-// V_g = fold( U . psi_g ) for the GS filters of one theta-group, written digit-swapped and
-// pre-scaled by 1/(F^2 * MC^2) (fold mean and inverse-FFT normalisation).
+// The aliases a in [0, F) for which index base + a*MC lies inside the cyclic span (lo << 16 | len) of a
+// length-MP axis are consecutive modulo F: {first, first+1, ...} (count of them).  Branch-free.
+struct AliasRun { int first, count; };
+template <int MP, int MC>
+WST_D AliasRun alias_run(int base, int packed) {
+    constexpr int F = MP / MC;
+    const int lo = packed >> 16, len = packed & 0xffff;
+    int t = lo - base;
+    t += t < 0 ? MP : 0;                              // distance from base up to the span start, cyclic
+    const int a0 = (t + MC - 1) / MC;                 // first alias at or after the span start (may equal F)
+    const int d0 = a0 * MC - t;                       // its offset inside the span, in [0, MC)
+    int cnt = d0 < len ? (len - 1 - d0) / MC + 1 : 0;
+    AliasRun r;
+    r.first = a0 >= F ? a0 - F : a0;
+    r.count = cnt > F ? F : cnt;
+    return r;
+}
+
+// V_g = fold( U . psi_g ) for the GS filters of one theta-group, written digit-swapped and pre-scaled by
+// 1/(F^2 * MC^2) (fold mean and inverse-FFT normalisation).
 //   uh   : parent half spectrum, side MP (shared or global memory)
-//   filt : [MP][MP][GS] real filters of this group
+//   filt : [MP][MP][GS] real filters of this group, orientations interleaved so that one vector load feeds
+//          GS accumulators and the index arithmetic is shared
+//   rows, cols : cyclic bounding box of the group's support.  psi^ of scale j is a Gaussian bump around the
+//          origin, so at fold factors >= 4 most aliases fall outside it.  The aliases inside are consecutive
+//          modulo F: rows are a short runtime loop, columns a fixed-length straight-line batch of NB loads
+//          starting at the first alias inside (extra ones only add exact zeros' worth of tail), so the loads
+//          of a row are independent and in flight together — these phases are L2-latency bound.
 //   out  : GS arrays of MC x MC (pitch MC+1, stride MC*(MC+1))
 template <int MP, int MC, int GS, int NT>
-WST_D void product_fold(int tid, const cfloat* uh, const float* filt, cfloat* out) {
+WST_D void product_fold(int tid, const cfloat* uh, const float* filt, int rows, int cols, cfloat* out) {
     constexpr int F = MP / MC, PC = MC + 1, AS = MC * (MC + 1);
+    constexpr bool SPARSE = F >= 4;
+    constexpr int NB = F >= 8 ? 4 : F;                // columns visited per row and batch
     constexpr float scale = 1.0f / ((float)F * (float)F * (float)MC * (float)MC);
     for (int o = tid; o < MC * MC; o += NT) {
         int lc = o % MC, kc = o / MC;
         float ar[GS], ai[GS];
         static_for<0, GS>([&](auto G) { ar[decltype(G)::value] = 0.f; ai[decltype(G)::value] = 0.f; });
-        for (int a = 0; a < F; ++a) {
-            int k = kc + a * MC;
-            for (int b = 0; b < F; ++b) {
-                int l = lc + b * MC;
-                cfloat u = herm_get<MP>(uh, k, l);
-                const float* fp = filt + ((size_t)k * MP + l) * GS;
-                float w[GS];
-                if constexpr (GS % 4 == 0) {
-                    static_for<0, GS / 4>([&](auto Q) {
-                        constexpr int q = decltype(Q)::value;
-                        float4 t = *reinterpret_cast<const float4*>(fp + 4 * q);
-                        w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+        AliasRun ra{0, F}, rb{0, F};
+        if constexpr (SPARSE) { ra = alias_run<MP, MC>(kc, rows); rb = alias_run<MP, MC>(lc, cols); }
+        if constexpr (!SPARSE || NB == F) { rb.first = 0; rb.count = (SPARSE && rb.count == 0) ? 0 : F; }
+        for (int ia = 0; ia < ra.count; ++ia) {
+            int a = ra.first + ia; a -= a >= F ? F : 0;
+            const int k = kc + a * MC;
+            for (int ib0 = 0; ib0 < rb.count; ib0 += NB) {
+                float w[NB][GS];
+                cfloat u[NB];
+                static_for<0, NB>([&](auto B) {
+                    constexpr int bi = decltype(B)::value;
+                    int b = rb.first + ib0 + bi; b -= b >= F ? F : 0;
+                    const int l = lc + b * MC;
+                    const float* fp = filt + ((size_t)k * MP + l) * GS;
+                    if constexpr (GS % 4 == 0) {
+                        static_for<0, GS / 4>([&](auto Q) {
+                            constexpr int q = decltype(Q)::value;
+                            float4 t = *reinterpret_cast<const float4*>(fp + 4 * q);
+                            w[bi][4 * q] = t.x; w[bi][4 * q + 1] = t.y; w[bi][4 * q + 2] = t.z; w[bi][4 * q + 3] = t.w;
+                        });
+                    } else if constexpr (GS == 2) {
+                        float2 t = *reinterpret_cast<const float2*>(fp);
+                        w[bi][0] = t.x; w[bi][1] = t.y;
+                    } else {
+                        static_for<0, GS>([&](auto G) { w[bi][decltype(G)::value] = fp[decltype(G)::value]; });
+                    }
+                    u[bi] = herm_get<MP>(uh, k, l);
+                });
+                static_for<0, NB>([&](auto B) {
+                    constexpr int bi = decltype(B)::value;
+                    static_for<0, GS>([&](auto G) {
+                        constexpr int g = decltype(G)::value;
+                        ar[g] += u[bi].x * w[bi][g];
+                        ai[g] += u[bi].y * w[bi][g];
                     });
-                } else if constexpr (GS == 2) {
-                    float2 t = *reinterpret_cast<const float2*>(fp);
-                    w[0] = t.x; w[1] = t.y;
-                } else {
-                    static_for<0, GS>([&](auto G) { w[decltype(G)::value] = fp[decltype(G)::value]; });
-                }
-                static_for<0, GS>([&](auto G) {
-                    constexpr int g = decltype(G)::value;
-                    ar[g] += u.x * w[g];
-                    ai[g] += u.y * w[g];
                 });
             }
         }
@@ -432,6 +560,27 @@ WST_D void lowpass_maps(Exec& ex, cfloat* z, int ZS, int narr, const float* gr, 
     });
 }
 
+// Inverse 2-D FFT of narr digit-swapped M x M spectra (pitch M+1) + modulus (+ row-paired z for a following
+// rfft2_from_pairs) + low-pass map of every array.
+template <int M, int NT, int LV, bool WRITE_Z, int HOUT, int HP, int LPSLOTS, class Exec, class CoefFn>
+WST_D void ifft2_modulus_lowpass(Exec& ex, cfloat* base, int narr, const cfloat* tw, const float* g,
+                                 float* lpbuf, float* maps, CoefFn coef) {
+    constexpr int P = M + 1, AS = M * (M + 1);
+    constexpr bool FUSED = (Fft1<M>::R1 == 1) ? !WRITE_Z
+                                              : (WRITE_Z ? (HOUT <= Fft1<M>::R1) : (HOUT / 2 <= Fft1<M>::R1));
+    fft_lines_inv<M, M, 1, P, NT, PK_IFFT_COL_C * 8 + LV, PK_IFFT_COL_S * 8 + LV>(ex, base, narr, AS, tw);   // columns
+    if constexpr (Fft1<M>::R1 > 1) {
+        ex.template phase<PK_IFFT_ROW_C * 8 + LV>([&](int tid) { pass_contig<M, +1, true, M, P, 1, NT>(tid, base, narr, AS, tw); });
+    }
+    if constexpr (FUSED) {
+        ex.template phase<PK_IFFT_FINAL * 8 + LV>([&](int tid) { pass_rows_final<M, NT, WRITE_Z, true, HOUT, HP>(tid, base, narr, AS, g); });
+        lowpass_reduce<M, NT, WRITE_Z, HOUT, HP, LPSLOTS, LV>(ex, base, narr, AS, g, lpbuf, maps, coef);
+    } else {
+        ex.template phase<PK_IFFT_FINAL * 8 + LV>([&](int tid) { pass_rows_final<M, NT, true, false, HOUT, HP>(tid, base, narr, AS, g); });
+        lowpass_maps<M, HOUT, HP, NT, LV>(ex, base, AS, narr, g, g, maps, coef);
+    }
+}
+
 // ------------------------------------------------------------------ the per-signal program
 template <class C, class Exec>
 struct Cascade {
@@ -441,10 +590,13 @@ struct Cascade {
     const PlanTables& pt;
     cfloat* sm;          // shared data region (C::smem_cfloats())
     cfloat* twsm;        // shared twiddles   (C::tw_total)
+    float* gsm;          // shared low-pass operators (C::g_total)
+    float* lpbuf;        // shared scratch of the fused low-pass reduction (C::lpbuf_floats())
     cfloat* u0h;         // per-CTA global scratch: N * (N/2+1)
     float* maps;         // this signal's output maps [K][HOUT][HOUT]
 
     WST_D const cfloat* tw(int j) const { return twsm + C::tw_offset(j); }
+    WST_D const float* g(int j) const { return gsm + C::g_offset(j); }
 
     // index of the first order-2 coefficient of parent (j1, t1)
     WST_D int order2_base(int j1, int t1) const {
@@ -460,6 +612,7 @@ struct Cascade {
                 constexpr int j = decltype(Jj)::value;
                 constexpr int m = C::msize(j);
                 for (int i = tid; i < m; i += NT) twsm[C::tw_offset(j) + i] = pt.tw[j][i];
+                for (int i = tid; i < m * HP; i += NT) gsm[C::g_offset(j) + i] = pt.gr[j][i];
             });
         });
     }
@@ -477,7 +630,7 @@ struct Cascade {
                 sm[r * P + c] = cmake(x[r0 * W + sc], x[r1 * W + sc]);
             }
         });
-        lowpass_maps<N, HOUT, HP, NT, 0>(ex, sm, 0, 1, pt.gr[0], pt.gc[0], maps, [](int) { return 0; });
+        lowpass_maps<N, HOUT, HP, NT, 0>(ex, sm, 0, 1, g(0), g(0), maps, [](int) { return 0; });
         cfloat* uh = sm + C::OFFB(0);
         rfft2_from_pairs<N, NT, 0>(ex, sm, 0, uh, 1, tw(0));
         ex.template phase<PK_U0_STORE * 8>([&](int tid) {
@@ -492,11 +645,13 @@ struct Cascade {
         const int ngroups = (L + G - 1) / G;
         const int cbase = order2_base(J1, t1) + (J2 - J1 - 1) * L;
         for (int grp = 0; grp < ngroups; ++grp) {
-            const float* filt = pt.psi2[J2][J1] + (size_t)grp * MP * MP * G;
-            ex.template phase<PK_PROD2 * 8 + J2>([&](int tid) { product_fold<MP, MC, G, NT>(tid, uh_parent, filt, sm); });
-            ifft2_modulus_pair<MC, NT, J2>(ex, sm, G, tw(J2));
-            lowpass_maps<MC, HOUT, HP, NT, J2>(ex, sm, C::vsz(MC), G, pt.gr[J2], pt.gc[J2], maps,
-                                           [&](int g) { int t2 = grp * G + g; return t2 < L ? cbase + t2 : -1; });
+            ex.template phase<PK_PROD2 * 8 + J2>([&](int tid) {
+                product_fold<MP, MC, G, NT>(tid, uh_parent, pt.psi2[J2][J1] + (size_t)grp * MP * MP * G,
+                                            pt.bb2[pair_index(J2, J1)][grp][0], pt.bb2[pair_index(J2, J1)][grp][1], sm);
+            });
+            ifft2_modulus_lowpass<MC, NT, J2, false, HOUT, HP, C::LP_SLOTS>(
+                ex, sm, G, tw(J2), g(J2), lpbuf, maps,
+                [&](int a) { int t2 = grp * G + a; return t2 < L ? cbase + t2 : -1; });
         }
     }
 
@@ -506,11 +661,13 @@ struct Cascade {
         const int L = pt.L;
         const int ngroups = (L + GPn - 1) / GPn;
         for (int grp = 0; grp < ngroups; ++grp) {
-            const float* filt = pt.psi1[J1] + (size_t)grp * N * N * GPn;
-            ex.template phase<PK_PROD1 * 8 + J1>([&](int tid) { product_fold<N, M, GPn, NT>(tid, u0h, filt, sm); });
-            ifft2_modulus_pair<M, NT, J1>(ex, sm, GPn, tw(J1));
-            lowpass_maps<M, HOUT, HP, NT, J1>(ex, sm, C::vsz(M), GPn, pt.gr[J1], pt.gc[J1], maps,
-                                          [&](int g) { int t1 = grp * GPn + g; return t1 < L ? 1 + J1 * L + t1 : -1; });
+            ex.template phase<PK_PROD1 * 8 + J1>([&](int tid) {
+                product_fold<N, M, GPn, NT>(tid, u0h, pt.psi1[J1] + (size_t)grp * N * N * GPn,
+                                            pt.bb1[J1][grp][0], pt.bb1[J1][grp][1], sm);
+            });
+            ifft2_modulus_lowpass<M, NT, J1, C::has_children(J1), HOUT, HP, C::LP_SLOTS>(
+                ex, sm, GPn, tw(J1), g(J1), lpbuf, maps,
+                [&](int a) { int t1 = grp * GPn + a; return t1 < L ? 1 + J1 * L + t1 : -1; });
             if constexpr (C::has_children(J1)) {
                 if (pt.max_order >= 2) {
                     cfloat* uh = sm + C::OFFB(J1);

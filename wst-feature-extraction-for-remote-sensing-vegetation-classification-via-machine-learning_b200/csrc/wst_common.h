@@ -43,7 +43,9 @@ WST_HD cfloat cmul_i(cfloat a) { return make_float2(-a.y, a.x); }    // a * (+i)
 WST_HD cfloat cmul_ni(cfloat a) { return make_float2(a.y, -a.x); }   // a * (-i)
 WST_HD float cabs_(cfloat a) {
 #ifdef __CUDA_ARCH__
-    return sqrtf(fmaf(a.x, a.x, a.y * a.y));
+    float s = fmaf(a.x, a.x, a.y * a.y), r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(s));      // MUFU.SQRT, ~1 ulp, sqrt(0) = 0
+    return r;
 #else
     return sqrtf(a.x * a.x + a.y * a.y);
 #endif

@@ -47,10 +47,12 @@ cascade_kernel(const PlanTables pt, const float* __restrict__ x, long long nsig,
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cfloat* sm = reinterpret_cast<cfloat*>(smem_raw);
     cfloat* twsm = sm + C::smem_cfloats();
+    float* gsm = reinterpret_cast<float*>(twsm + C::tw_total);
+    float* lpbuf = gsm + C::g_total;
     DevExec ex;
     const size_t sig_elems = (size_t)pt.H * pt.W;
     const size_t map_elems = (size_t)pt.K * C::HOUT * C::HOUT;
-    Cascade<C, DevExec> prog{ex, pt, sm, twsm,
+    Cascade<C, DevExec> prog{ex, pt, sm, twsm, gsm, lpbuf,
                              u0h_scratch + (size_t)blockIdx.x * (C::N * (C::N / 2 + 1)), nullptr};
     prog.load_twiddles();
     for (long long s = blockIdx.x; s < nsig; s += gridDim.x) {
@@ -69,12 +71,14 @@ cascade_prof_kernel(const PlanTables pt, const float* __restrict__ x, long long 
     __shared__ long long acc[kNumPhaseTags];
     cfloat* sm = reinterpret_cast<cfloat*>(smem_raw);
     cfloat* twsm = sm + C::smem_cfloats();
+    float* gsm = reinterpret_cast<float*>(twsm + C::tw_total);
+    float* lpbuf = gsm + C::g_total;
     for (int i = threadIdx.x; i < kNumPhaseTags; i += C::NT) acc[i] = 0;
     __syncthreads();
     ProfExec ex{acc};
     const size_t sig_elems = (size_t)pt.H * pt.W;
     const size_t map_elems = (size_t)pt.K * C::HOUT * C::HOUT;
-    Cascade<C, ProfExec> prog{ex, pt, sm, twsm,
+    Cascade<C, ProfExec> prog{ex, pt, sm, twsm, gsm, lpbuf,
                               u0h_scratch + (size_t)blockIdx.x * (C::N * (C::N / 2 + 1)), nullptr};
     prog.load_twiddles();
     for (long long s = blockIdx.x; s < nsig; s += gridDim.x) {
@@ -226,6 +230,7 @@ cudaError_t launch_cascade_prof(const PlanTables& pt, const float* x, long long 
 
 template <class C>
 CfgOps make_ops() {
+    static_assert(C::smem_bytes() + kNumPhaseTags * 8 <= 232448, "configuration exceeds the 227 KB of shared memory a CTA may use");
     CfgOps o;
     o.N = C::N; o.J = C::J; o.NT = C::NT; o.hout = C::HOUT;
     o.smem = C::smem_bytes();
@@ -403,6 +408,7 @@ int wst2d_plan_create(wst2d_plan** out, int device, int H, int W, int J, int L, 
         return fail(WST2D_ERR_ARG, "invalid plan arguments");
     if ((1 << J) > H || (1 << J) > W)
         return fail(WST2D_ERR_ARG, "The smallest dimension should be larger than 2^J.");
+    if (L > kMaxL) return fail(WST2D_ERR_UNSUPPORTED, "more than 8 orientations (L) is not supported by the compiled cascades");
     const int Hp = padded_size(H, J), Wp = padded_size(W, J);
     const CfgOps* ops = nullptr;
     if (Hp == Wp)
@@ -448,6 +454,13 @@ int wst2d_plan_create(wst2d_plan** out, int device, int H, int W, int J, int L, 
         return fail(WST2D_ERR_CUDA, "cascade kernel setup: " + m);
     }
     p->grid_max = sms * per_sm;
+    {   // keep the stream-ordered scratch (cudaMallocAsync in forward) cached across synchronisations
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
     *out = p;
     return WST2D_OK;
 }

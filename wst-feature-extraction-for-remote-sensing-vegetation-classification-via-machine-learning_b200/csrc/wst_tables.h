@@ -19,6 +19,8 @@ namespace wst {
 struct TableOffsets {              // offsets in floats into the flat buffer
     size_t tw[kMaxJ], gr[kMaxJ], gc[kMaxJ], psi1[kMaxJ], psi2[kMaxJ][kMaxJ];
     size_t total;
+    int bb1[kMaxJ][kMaxL][2], bb2[kMaxPairs][kMaxL][2];    // support bounding boxes (copied into PlanTables)
+    double support_fraction;      // visited filter entries / all filter entries (diagnostic)
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -45,11 +47,13 @@ inline bool build_tables(int L, const float* psi_hat, const float* phi_hat,
         gp[j] = C::GP(j);
         static_for<j + 1, J>([&](auto J2c) { constexpr int j2 = decltype(J2c)::value; g2[j2][j] = C::G2(j, j2); });
     });
-    for (int j = 0; j < J; ++j) off.psi1[j] = reserve((size_t)groups(L, gp[j]) * gp[j] * N * N);
+    int vw1[kMaxJ], vw2[kMaxJ][kMaxJ];          // interleave width = theta-group size
+    for (int j = 0; j < J; ++j) { vw1[j] = gp[j]; for (int j2 = j + 1; j2 < J; ++j2) vw2[j2][j] = g2[j2][j]; }
+    for (int j = 0; j < J; ++j) off.psi1[j] = reserve((size_t)groups(L, vw1[j]) * vw1[j] * N * N);
     for (int j2 = 1; j2 < J; ++j2)
         for (int j1 = 0; j1 < j2; ++j1) {
             int m = N >> j1;
-            off.psi2[j2][j1] = reserve((size_t)groups(L, g2[j2][j1]) * g2[j2][j1] * m * m);
+            off.psi2[j2][j1] = reserve((size_t)groups(L, vw2[j2][j1]) * vw2[j2][j1] * m * m);
         }
     off.total = cur;
     buf.assign(cur, 0.0f);
@@ -88,7 +92,8 @@ inline bool build_tables(int L, const float* psi_hat, const float* phi_hat,
             std::vector<double> a(m), g(m);
             for (int k = 0; k < m; ++k) {
                 int kk = (k < m / 2) ? k : N - m + k;
-                a[k] = (dim == 0 ? (double)phi_hat[(size_t)kk * N] : (double)phi_hat[kk]) * rs;
+                // square grid: one operator serves rows and columns (mean of phi^'s first column and first row)
+                a[k] = 0.5 * ((double)phi_hat[(size_t)kk * N] + (double)phi_hat[kk]) * rs;
             }
             for (int x = 0; x < m; ++x) {
                 double acc = 0.0;
@@ -104,32 +109,70 @@ inline bool build_tables(int L, const float* psi_hat, const float* phi_hat,
         }
     }
 
-    // ---- wavelets, periodised per level and theta-interleaved
-    auto fill = [&](float* dst, int j, int res, int g) {
+    // ---- wavelets, periodised per level (planar), with their supports
+    // smallest cyclic interval of [0, n) covering all flagged positions, packed lo << 16 | len
+    auto cyclic_span = [](const std::vector<char>& on) -> int {
+        int n = (int)on.size(), first = -1, cnt = 0;
+        for (int i = 0; i < n; ++i) if (on[i]) { if (first < 0) first = i; ++cnt; }
+        if (cnt == 0) return 0;
+        if (cnt == n) return n;                                   // lo = 0, len = n
+        int best_gap = -1, best_end = 0, prev = -1, last = 0;     // largest run of unflagged positions (cyclic)
+        for (int i = 0; i < n; ++i) if (on[i]) last = i;
+        prev = last - n;
+        for (int i = 0; i < n; ++i) if (on[i]) {
+            int gap = i - prev - 1;
+            if (gap > best_gap) { best_gap = gap; best_end = i; }
+            prev = i;
+        }
+        int lo = best_end, len = n - best_gap;
+        return (lo << 16) | len;
+    };
+    double visited = 0.0, all = 0.0;
+    auto fill = [&](size_t ofilt, int (*bb)[2], int j, int res, int vw) {
         int m = N >> res;
-        int ng = groups(L, g);
-        for (int grp = 0; grp < ng; ++grp)
-            for (int t = 0; t < g; ++t) {
-                int theta = grp * g + t;
-                if (theta >= L) continue;
+        float* dst = buf.data() + ofilt;
+        int nvg = groups(L, vw);
+        for (int vg = 0; vg < nvg; ++vg) {
+            std::vector<char> rowon(m, 0), colon(m, 0);
+            for (int e = 0; e < vw; ++e) {
+                int theta = vg * vw + e;
+                if (theta >= L) continue;                          // padding orientations stay zero
                 const float* src = psi_hat + (size_t)(j * L + theta) * N * N;
+                float mx = 0.f;
                 for (int k = 0; k < m; ++k) {
                     int kk = (k < m / 2) ? k : N - m + k;
                     for (int l = 0; l < m; ++l) {
                         int ll = (l < m / 2) ? l : N - m + l;
-                        dst[(((size_t)grp * m + k) * m + l) * g + t] = src[(size_t)kk * N + ll];
+                        float v = src[(size_t)kk * N + ll];
+                        dst[(((size_t)vg * m + k) * m + l) * vw + e] = v;
+                        if (std::fabs(v) > mx) mx = std::fabs(v);
                     }
                 }
+                const float thr = kSupportEps * mx;
+                for (int k = 0; k < m; ++k)
+                    for (int l = 0; l < m; ++l)
+                        if (std::fabs(dst[(((size_t)vg * m + k) * m + l) * vw + e]) > thr) { rowon[k] = 1; colon[l] = 1; }
             }
+            bb[vg][0] = cyclic_span(rowon);
+            bb[vg][1] = cyclic_span(colon);
+            visited += (double)(bb[vg][0] & 0xffff) * (double)(bb[vg][1] & 0xffff) * vw;
+            all += (double)m * m * vw;
+        }
     };
-    for (int j = 0; j < J; ++j) fill(buf.data() + off.psi1[j], j, 0, gp[j]);
+    if (L > kMaxL) { err = "L > " + std::to_string(kMaxL) + " orientations is not supported by the compiled cascades"; return false; }
+    std::memset(off.bb1, 0, sizeof(off.bb1));
+    std::memset(off.bb2, 0, sizeof(off.bb2));
+    for (int j = 0; j < J; ++j) fill(off.psi1[j], off.bb1[j], j, 0, vw1[j]);
     for (int j2 = 1; j2 < J; ++j2)
-        for (int j1 = 0; j1 < j2; ++j1) fill(buf.data() + off.psi2[j2][j1], j2, j1, g2[j2][j1]);
+        for (int j1 = 0; j1 < j2; ++j1) fill(off.psi2[j2][j1], off.bb2[pair_index(j2, j1)], j2, j1, vw2[j2][j1]);
+    off.support_fraction = all > 0 ? visited / all : 1.0;
     return true;
 }
 
 template <class C>
 inline void bind_tables(PlanTables& pt, const float* base, const TableOffsets& off) {
+    std::memcpy(pt.bb1, off.bb1, sizeof(pt.bb1));
+    std::memcpy(pt.bb2, off.bb2, sizeof(pt.bb2));
     for (int j = 0; j < C::J; ++j) {
         pt.tw[j] = reinterpret_cast<const cfloat*>(base + off.tw[j]);
         pt.gr[j] = base + off.gr[j];
