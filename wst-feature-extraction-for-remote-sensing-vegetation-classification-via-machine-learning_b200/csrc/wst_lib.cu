@@ -13,6 +13,7 @@
 // There is no CPU fallback anywhere in this file: without a CUDA device plan creation fails.
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -269,6 +270,18 @@ struct wst2d_plan {
     mutable std::mutex prof_mu;
     mutable bool profiling = false;
     mutable std::vector<cudaEvent_t> prof_cascade, prof_pool;   // (start, stop) pairs
+    // resources of the host-buffer path (wst2d_forward_host), created on first use and reused:
+    // two streams, each with its staging input / feature buffers and its cascade scratch
+    struct HostPath {
+        std::mutex mu;
+        cudaStream_t st[2] = {nullptr, nullptr};
+        float* x[2] = {nullptr, nullptr};
+        float* f[2] = {nullptr, nullptr};
+        cfloat* u0h[2] = {nullptr, nullptr};
+        float* maps[2] = {nullptr, nullptr};
+        long long cap_sig = 0;        // signals per chunk the buffers are sized for
+    };
+    mutable HostPath host;
 };
 
 namespace {
@@ -354,17 +367,19 @@ long long chunk_signals(const wst2d_plan* p, long long nsig) {
     return c;
 }
 
+// own_u0h / own_maps: caller-provided scratch (host path) sized for grid_max CTAs / nsig signals; when NULL
+// the scratch is stream-ordered (cudaMallocAsync from the device's default pool).
 int forward_impl(const wst2d_plan* p, const float* x_dev, long long nsig, float* feats_dev,
-                 float* maps_dev, cudaStream_t st) {
+                 float* maps_dev, cudaStream_t st, cfloat* own_u0h = nullptr, float* own_maps = nullptr) {
     if (nsig == 0) return WST2D_OK;
     const size_t sig_elems = (size_t)p->H * p->W;
     const size_t map_elems = (size_t)p->K * p->hout * p->hout;
     const size_t u0h_elems = (size_t)p->N * (p->N / 2 + 1);
-    const long long chunk = maps_dev ? nsig : chunk_signals(p, nsig);
+    const long long chunk = (maps_dev || own_maps) ? nsig : chunk_signals(p, nsig);
     const int grid_all = (int)(nsig < p->grid_max ? nsig : p->grid_max);
-    cfloat* d_u0h = nullptr; float* d_maps = nullptr;
-    CUDA_TRY(cudaMallocAsync(&d_u0h, (size_t)grid_all * u0h_elems * sizeof(cfloat), st));
-    if (!maps_dev) {
+    cfloat* d_u0h = own_u0h; float* d_maps = own_maps;
+    if (!own_u0h) CUDA_TRY(cudaMallocAsync(&d_u0h, (size_t)grid_all * u0h_elems * sizeof(cfloat), st));
+    if (!maps_dev && !own_maps) {
         cudaError_t e = cudaMallocAsync(&d_maps, (size_t)chunk * map_elems * sizeof(float), st);
         if (e != cudaSuccess) { cudaFreeAsync(d_u0h, st); return fail(WST2D_ERR_CUDA, std::string("cudaMallocAsync(maps): ") + cudaGetErrorString(e)); }
     }
@@ -389,8 +404,8 @@ int forward_impl(const wst2d_plan* p, const float* x_dev, long long nsig, float*
             if (e != cudaSuccess) { rc = fail(WST2D_ERR_CUDA, std::string("pool launch: ") + cudaGetErrorString(e)); break; }
         }
     }
-    cudaFreeAsync(d_u0h, st);
-    if (d_maps) cudaFreeAsync(d_maps, st);
+    if (!own_u0h) cudaFreeAsync(d_u0h, st);
+    if (d_maps && !own_maps) cudaFreeAsync(d_maps, st);
     return rc;
 }
 
@@ -468,6 +483,10 @@ int wst2d_plan_create(wst2d_plan** out, int device, int H, int W, int J, int L, 
 int wst2d_plan_destroy(wst2d_plan* plan) {
     if (!plan) return WST2D_OK;
     DeviceGuard guard(plan->device);
+    for (int i = 0; i < 2; ++i) {
+        if (plan->host.st[i]) { cudaStreamSynchronize(plan->host.st[i]); cudaStreamDestroy(plan->host.st[i]); }
+        cudaFree(plan->host.x[i]); cudaFree(plan->host.f[i]); cudaFree(plan->host.u0h[i]); cudaFree(plan->host.maps[i]);
+    }
     cudaFree(plan->d_tables);
     delete plan;
     return WST2D_OK;
@@ -520,46 +539,50 @@ int wst2d_forward_host(const wst2d_plan* p, const float* x_host, int64_t B, int 
     if (B == 0) return WST2D_OK;
     if (!x_host || !feats_host) return fail(WST2D_ERR_ARG, "host buffer is NULL");
     DeviceGuard guard(p->device);
-    const size_t patch_in = (size_t)C * p->H * p->W, patch_out = (size_t)C * 2 * p->K;
-    // chunk: a few persistent-grid waves per copy so that H2D, compute and D2H overlap
-    long long chunk = (long long)p->grid_max * 8 / C;
-    if (chunk < 1) chunk = 1;
-    if (chunk > B) chunk = B;
-    cudaStream_t st[2] = {nullptr, nullptr};
-    float* d_x[2] = {nullptr, nullptr}; float* d_f[2] = {nullptr, nullptr};
-    int rc = WST2D_OK;
-    auto cleanup = [&]() {
+    wst2d_plan::HostPath& hp = p->host;
+    std::lock_guard<std::mutex> lk(hp.mu);
+    const size_t sig_in = (size_t)p->H * p->W, sig_out = (size_t)2 * p->K;
+    const size_t map_elems = (size_t)p->K * p->hout * p->hout;
+    // chunk: a few persistent-grid waves per copy so that H2D, compute and D2H of neighbouring chunks overlap
+    long long chunk_sig = (long long)p->grid_max * 6;
+    if (const char* ev = getenv("WST_HOST_CHUNK_SIGNALS")) chunk_sig = atoll(ev);
+    chunk_sig = chunk_sig / C * C;
+    if (chunk_sig < C) chunk_sig = C;
+    if (chunk_sig > B * C) chunk_sig = B * C;
+    if (hp.cap_sig < chunk_sig) {           // (re)size the cached staging buffers; first call or larger C
         for (int i = 0; i < 2; ++i) {
-            if (st[i]) cudaStreamSynchronize(st[i]);
-            cudaFree(d_x[i]); cudaFree(d_f[i]);
-            if (st[i]) cudaStreamDestroy(st[i]);
+            if (hp.st[i]) cudaStreamSynchronize(hp.st[i]);
+            cudaFree(hp.x[i]); cudaFree(hp.f[i]); cudaFree(hp.u0h[i]); cudaFree(hp.maps[i]);
+            hp.x[i] = hp.f[i] = hp.maps[i] = nullptr; hp.u0h[i] = nullptr;
         }
-    };
-    for (int i = 0; i < 2 && rc == WST2D_OK; ++i) {
-        if (cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking) != cudaSuccess ||
-            cudaMalloc(&d_x[i], chunk * patch_in * sizeof(float)) != cudaSuccess ||
-            cudaMalloc(&d_f[i], chunk * patch_out * sizeof(float)) != cudaSuccess)
-            rc = fail(WST2D_ERR_CUDA, std::string("forward_host setup: ") + cudaGetErrorString(cudaGetLastError()));
+        hp.cap_sig = 0;
+        for (int i = 0; i < 2; ++i) {
+            if (!hp.st[i]) CUDA_TRY(cudaStreamCreateWithFlags(&hp.st[i], cudaStreamNonBlocking));
+            CUDA_TRY(cudaMalloc(&hp.x[i], chunk_sig * sig_in * sizeof(float)));
+            CUDA_TRY(cudaMalloc(&hp.f[i], chunk_sig * sig_out * sizeof(float)));
+            CUDA_TRY(cudaMalloc(&hp.u0h[i], (size_t)p->grid_max * p->N * (p->N / 2 + 1) * sizeof(cfloat)));
+            CUDA_TRY(cudaMalloc(&hp.maps[i], chunk_sig * map_elems * sizeof(float)));
+        }
+        hp.cap_sig = chunk_sig;
     }
-    int it = 0;
-    for (long long b0 = 0; b0 < B && rc == WST2D_OK; b0 += chunk, ++it) {
-        long long n = B - b0 < chunk ? B - b0 : chunk;
+    int rc = WST2D_OK, it = 0;
+    const long long nsig = (long long)B * C;
+    for (long long s0 = 0; s0 < nsig && rc == WST2D_OK; s0 += chunk_sig, ++it) {
+        long long n = nsig - s0 < chunk_sig ? nsig - s0 : chunk_sig;
         int i = it & 1;
-        cudaError_t e = cudaMemcpyAsync(d_x[i], x_host + (size_t)b0 * patch_in, n * patch_in * sizeof(float),
-                                        cudaMemcpyHostToDevice, st[i]);
+        cudaError_t e = cudaMemcpyAsync(hp.x[i], x_host + (size_t)s0 * sig_in, n * sig_in * sizeof(float),
+                                        cudaMemcpyHostToDevice, hp.st[i]);
         if (e != cudaSuccess) { rc = fail(WST2D_ERR_CUDA, std::string("H2D: ") + cudaGetErrorString(e)); break; }
-        rc = forward_impl(p, d_x[i], n * C, d_f[i], nullptr, st[i]);
+        rc = forward_impl(p, hp.x[i], n, hp.f[i], nullptr, hp.st[i], hp.u0h[i], hp.maps[i]);
         if (rc != WST2D_OK) break;
-        e = cudaMemcpyAsync(feats_host + (size_t)b0 * patch_out, d_f[i], n * patch_out * sizeof(float),
-                            cudaMemcpyDeviceToHost, st[i]);
+        e = cudaMemcpyAsync(feats_host + (size_t)s0 * sig_out, hp.f[i], n * sig_out * sizeof(float),
+                            cudaMemcpyDeviceToHost, hp.st[i]);
         if (e != cudaSuccess) { rc = fail(WST2D_ERR_CUDA, std::string("D2H: ") + cudaGetErrorString(e)); break; }
     }
-    for (int i = 0; i < 2; ++i)
-        if (st[i]) {
-            cudaError_t e = cudaStreamSynchronize(st[i]);
-            if (e != cudaSuccess && rc == WST2D_OK) rc = fail(WST2D_ERR_CUDA, std::string("forward_host sync: ") + cudaGetErrorString(e));
-        }
-    cleanup();
+    for (int i = 0; i < 2; ++i) {
+        cudaError_t e = cudaStreamSynchronize(hp.st[i]);
+        if (e != cudaSuccess && rc == WST2D_OK) rc = fail(WST2D_ERR_CUDA, std::string("forward_host sync: ") + cudaGetErrorString(e));
+    }
     return rc;
 }
 
