@@ -44,7 +44,8 @@ constexpr int kSmemCfloats = 27000;      // data region budget (216,000 B) of th
 
 // ------------------------------------------------------------------ 1-D factorisation n = R1*R2
 WST_CX int fft_R2(int n) {               // contiguous radix
-    if (n <= 20) return n;
+    if (n <= 18) return n;                 // one in-register pass
+    if (n == 20) return 5;                 // 4 x 5: more, smaller butterflies keep 512 threads busy on 20 x 20 arrays
     int odd = n; while (odd % 2 == 0) odd /= 2;
     int best = 0; long best_score = 1L << 60;
     for (int r2 = odd; r2 <= 24 && r2 <= n; r2 *= 2) {
@@ -339,7 +340,7 @@ WST_D void lowpass_reduce(Exec& ex, cfloat* base, int narr, int AS, const float*
     constexpr int R1 = Fft1<M>::R1, R2 = Fft1<M>::R2, P = M + 1, HALF = M / 2;
     constexpr int NSUB = (R1 > 1) ? R2 : 1, YS = (R1 > 1) ? R2 : 1;
     int nchunks = LPSLOTS / narr;
-    if (nchunks > (M + 7) / 8) nchunks = (M + 7) / 8;
+    if (nchunks > (M + 3) / 4) nchunks = (M + 3) / 4;
     if (nchunks < 1) nchunks = 1;
     const int rc = (M + nchunks - 1) / nchunks;
     ex.template phase<PK_LPR * 8 + LV>([&](int tid) {
@@ -445,59 +446,104 @@ WST_D AliasRun alias_run(int base, int packed) {
 //          starting at the first alias inside (extra ones only add exact zeros' worth of tail), so the loads
 //          of a row are independent and in flight together — these phases are L2-latency bound.
 //   out  : GS arrays of MC x MC (pitch MC+1, stride MC*(MC+1))
+template <int MP, int GS>
+WST_D void load_filter_vec(const float* fp, float (&w)[GS]) {
+    if constexpr (GS % 4 == 0) {
+        static_for<0, GS / 4>([&](auto Q) {
+            constexpr int q = decltype(Q)::value;
+            float4 t = *reinterpret_cast<const float4*>(fp + 4 * q);
+            w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+        });
+    } else if constexpr (GS == 2) {
+        float2 t = *reinterpret_cast<const float2*>(fp);
+        w[0] = t.x; w[1] = t.y;
+    } else {
+        static_for<0, GS>([&](auto G) { w[decltype(G)::value] = fp[decltype(G)::value]; });
+    }
+}
+
 template <int MP, int MC, int GS, int NT>
 WST_D void product_fold(int tid, const cfloat* uh, const float* filt, int rows, int cols, cfloat* out) {
     constexpr int F = MP / MC, PC = MC + 1, AS = MC * (MC + 1);
     constexpr bool SPARSE = F >= 4;
-    constexpr int NB = F >= 8 ? 4 : F;                // columns visited per row and batch
     constexpr float scale = 1.0f / ((float)F * (float)F * (float)MC * (float)MC);
-    for (int o = tid; o < MC * MC; o += NT) {
-        int lc = o % MC, kc = o / MC;
-        float ar[GS], ai[GS];
-        static_for<0, GS>([&](auto G) { ar[decltype(G)::value] = 0.f; ai[decltype(G)::value] = 0.f; });
-        AliasRun ra{0, F}, rb{0, F};
-        if constexpr (SPARSE) { ra = alias_run<MP, MC>(kc, rows); rb = alias_run<MP, MC>(lc, cols); }
-        if constexpr (!SPARSE || NB == F) { rb.first = 0; rb.count = (SPARSE && rb.count == 0) ? 0 : F; }
-        for (int ia = 0; ia < ra.count; ++ia) {
-            int a = ra.first + ia; a -= a >= F ? F : 0;
-            const int k = kc + a * MC;
-            for (int ib0 = 0; ib0 < rb.count; ib0 += NB) {
-                float w[NB][GS];
-                cfloat u[NB];
-                static_for<0, NB>([&](auto B) {
-                    constexpr int bi = decltype(B)::value;
-                    int b = rb.first + ib0 + bi; b -= b >= F ? F : 0;
-                    const int l = lc + b * MC;
-                    const float* fp = filt + ((size_t)k * MP + l) * GS;
-                    if constexpr (GS % 4 == 0) {
-                        static_for<0, GS / 4>([&](auto Q) {
-                            constexpr int q = decltype(Q)::value;
-                            float4 t = *reinterpret_cast<const float4*>(fp + 4 * q);
-                            w[bi][4 * q] = t.x; w[bi][4 * q + 1] = t.y; w[bi][4 * q + 2] = t.z; w[bi][4 * q + 3] = t.w;
-                        });
-                    } else if constexpr (GS == 2) {
-                        float2 t = *reinterpret_cast<const float2*>(fp);
-                        w[bi][0] = t.x; w[bi][1] = t.y;
-                    } else {
-                        static_for<0, GS>([&](auto G) { w[bi][decltype(G)::value] = fp[decltype(G)::value]; });
-                    }
-                    u[bi] = herm_get<MP>(uh, k, l);
+    if constexpr (!SPARSE) {
+        // dense: all F*F aliases of U outputs per thread are loaded as one straight-line batch
+        constexpr int U = cx_max(1, cx_min(8, 32 / (F * F * (GS + 2))));
+        for (int o0 = tid; o0 < MC * MC; o0 += NT * U) {
+            float w[U][F * F][GS];
+            cfloat u[U][F * F];
+            int kc[U], lc[U];
+            static_for<0, U>([&](auto Uc) {
+                constexpr int ui = decltype(Uc)::value;
+                int o = o0 + ui * NT;
+                o = o < MC * MC ? o : MC * MC - 1;          // tail items recompute the last output, never stored
+                lc[ui] = o % MC; kc[ui] = o / MC;
+                static_for<0, F * F>([&](auto S) {
+                    constexpr int sl = decltype(S)::value;
+                    const int k = kc[ui] + (sl / F) * MC, l = lc[ui] + (sl % F) * MC;
+                    load_filter_vec<MP, GS>(filt + ((size_t)k * MP + l) * GS, w[ui][sl]);
+                    u[ui][sl] = herm_get<MP>(uh, k, l);
                 });
-                static_for<0, NB>([&](auto B) {
-                    constexpr int bi = decltype(B)::value;
+            });
+            static_for<0, U>([&](auto Uc) {
+                constexpr int ui = decltype(Uc)::value;
+                float ar[GS], ai[GS];
+                static_for<0, GS>([&](auto G) { ar[decltype(G)::value] = 0.f; ai[decltype(G)::value] = 0.f; });
+                static_for<0, F * F>([&](auto S) {
+                    constexpr int sl = decltype(S)::value;
                     static_for<0, GS>([&](auto G) {
                         constexpr int g = decltype(G)::value;
-                        ar[g] += u[bi].x * w[bi][g];
-                        ai[g] += u[bi].y * w[bi][g];
+                        ar[g] += u[ui][sl].x * w[ui][sl][g];
+                        ai[g] += u[ui][sl].y * w[ui][sl][g];
                     });
                 });
-            }
+                if (o0 + ui * NT < MC * MC) {
+                    cfloat* op = out + Fft1<MC>::pi(kc[ui]) * PC + Fft1<MC>::pi(lc[ui]);
+                    static_for<0, GS>([&](auto G) {
+                        constexpr int g = decltype(G)::value;
+                        op[g * AS] = cmake(ar[g] * scale, ai[g] * scale);
+                    });
+                }
+            });
         }
-        cfloat* op = out + Fft1<MC>::pi(kc) * PC + Fft1<MC>::pi(lc);
-        static_for<0, GS>([&](auto G) {
-            constexpr int g = decltype(G)::value;
-            op[g * AS] = cmake(ar[g] * scale, ai[g] * scale);
-        });
+    } else {
+        constexpr int NB = F >= 8 ? 4 : F;                // columns visited per row and batch
+        for (int o = tid; o < MC * MC; o += NT) {
+            int lc = o % MC, kc = o / MC;
+            float ar[GS], ai[GS];
+            static_for<0, GS>([&](auto G) { ar[decltype(G)::value] = 0.f; ai[decltype(G)::value] = 0.f; });
+            AliasRun ra = alias_run<MP, MC>(kc, rows), rb = alias_run<MP, MC>(lc, cols);
+            if constexpr (NB == F) { rb.first = 0; rb.count = rb.count == 0 ? 0 : F; }
+            for (int ia = 0; ia < ra.count; ++ia) {
+                int a = ra.first + ia; a -= a >= F ? F : 0;
+                const int k = kc + a * MC;
+                for (int ib0 = 0; ib0 < rb.count; ib0 += NB) {
+                    float w[NB][GS];
+                    cfloat u[NB];
+                    static_for<0, NB>([&](auto B) {
+                        constexpr int bi = decltype(B)::value;
+                        int b = rb.first + ib0 + bi; b -= b >= F ? F : 0;
+                        const int l = lc + b * MC;
+                        load_filter_vec<MP, GS>(filt + ((size_t)k * MP + l) * GS, w[bi]);
+                        u[bi] = herm_get<MP>(uh, k, l);
+                    });
+                    static_for<0, NB>([&](auto B) {
+                        constexpr int bi = decltype(B)::value;
+                        static_for<0, GS>([&](auto G) {
+                            constexpr int g = decltype(G)::value;
+                            ar[g] += u[bi].x * w[bi][g];
+                            ai[g] += u[bi].y * w[bi][g];
+                        });
+                    });
+                }
+            }
+            cfloat* op = out + Fft1<MC>::pi(kc) * PC + Fft1<MC>::pi(lc);
+            static_for<0, GS>([&](auto G) {
+                constexpr int g = decltype(G)::value;
+                op[g * AS] = cmake(ar[g] * scale, ai[g] * scale);
+            });
+        }
     }
 }
 
