@@ -80,7 +80,7 @@ int emu_fft2(int M, int dir, float* data) {
     switch (M) {
 #define CASE(m) case m: run(std::integral_constant<int, m>{}); return 0;
         CASE(6) CASE(10) CASE(12) CASE(18) CASE(20) CASE(24) CASE(34) CASE(36) CASE(40) CASE(48) CASE(64) CASE(68) CASE(72)
-        CASE(80) CASE(96) CASE(136) CASE(144) CASE(160)
+        CASE(80) CASE(96) CASE(136) CASE(144) CASE(160) CASE(288) CASE(576)
 #undef CASE
     }
     g_err = "emu_fft2: unsupported size";
@@ -91,8 +91,10 @@ int emu_fft2(int M, int dir, float* data) {
 int emu_forward(int N, int J, int L, int max_order, int H, int W, const float* psi_hat,
                 const float* phi_hat, const float* x, int nsig, float* maps_out) {
 #define CFG(n, j) if (N == n && J == j) return run_cfg<Cfg<n, j>>(L, max_order, H, W, psi_hat, phi_hat, x, nsig, maps_out, g_err);
+#define CFGG(n, j) if (N == n && J == j) return run_cfg<Cfg<n, j, 256, true>>(L, max_order, H, W, psi_hat, phi_hat, x, nsig, maps_out, g_err);
 #include "wst_configs.inc"
 #undef CFG
+#undef CFGG
     g_err = "emu_forward: unsupported (N, J)";
     return -2;
 }
@@ -135,11 +137,15 @@ int emu_filter_bank(int N, int J, int L, float* psi_hat, float* phi_hat) {
 }
 
 int emu_query(int N, int J, int* smem_bytes, int* gp, int* hout) {
-#define CFG(n, j) if (N == n && J == j) { using C = Cfg<n, j>; *smem_bytes = (int)C::smem_bytes(); *hout = C::HOUT; \
-        for (int i = 0; i < j; ++i) gp[i] = 0; \
-        static_for<0, j>([&](auto Jc) { gp[decltype(Jc)::value] = C::GP(decltype(Jc)::value); }); return 0; }
+#define CFGQ(C_) { using C = C_; *smem_bytes = (int)C::smem_bytes(); *hout = C::HOUT; \
+        for (int i = 0; i < C::J; ++i) gp[i] = 0; \
+        static_for<0, C::J>([&](auto Jc) { gp[decltype(Jc)::value] = C::GP(decltype(Jc)::value); }); return 0; }
+#define CFG(n, j) if (N == n && J == j) CFGQ(Cfg<n COMMA j>)
+#define CFGG(n, j) if (N == n && J == j) CFGQ(Cfg<n COMMA j COMMA 256 COMMA true>)
+#define COMMA ,
 #include "wst_configs.inc"
 #undef CFG
+#undef CFGG
     return -2;
 }
 

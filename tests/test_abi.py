@@ -43,6 +43,7 @@ def test_argument_validation(built_lib):
     assert built_lib.wst2d_plan_create(ctypes.byref(h), 0, 100, 100, 2, 8, 2) == -2        # no compiled cascade
     assert b"no compiled cascade" in built_lib.wst2d_last_error()
     assert built_lib.wst2d_plan_create(ctypes.byref(h), 0, 32, 64, 2, 8, 2) == -2          # non-square
+    assert built_lib.wst2d_plan_create(ctypes.byref(h), 0, 32, 32, 2, 16, 2) == -2         # L > 8
     assert built_lib.wst2d_query(None, None, None, None, None, None) == -1
     assert built_lib.wst2d_forward(None, None, 1, 1, None, None, None) == -1
     assert built_lib.wst2d_plan_destroy(None) == 0

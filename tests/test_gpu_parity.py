@@ -111,6 +111,24 @@ def test_golden_vectors(wst, tag, J, L):
         assert floored_rel(maps.cpu().numpy()[:, 0].reshape(10, -1), g["maps64"].reshape(10, -1)) <= TOL
 
 
+def test_cfg5_512_J5_multispectral(wst):
+    """BASELINE configs[4]: 512x512, J=5, L=8, C=4 tiles (padded side 576 = 24*24: global-workspace cascade)."""
+    rng = np.random.default_rng(11)
+    x = (rng.integers(0, 256, (1, 4, 512, 512)) / 255.0).astype(np.float32)
+    plan = wst.get_plan(512, 512, 5, 8)
+    assert (plan.K, plan.h, plan.Hp) == (681, 16, 576)
+    feats, maps = plan.forward(torch.from_numpy(x).cuda(), True, True)
+    assert tuple(feats.shape) == (1, 4, 2, 681)
+    ref = oracle64(512, 5, 8)(x[0, :2])                       # two channels keep the CPU oracle at a few seconds
+    assert floored_rel(maps[0, :2].cpu().numpy().reshape(2, -1), ref.reshape(2, -1)) <= TOL
+    f = feats[0, :2].cpu().numpy()
+    assert floored_rel(f[:, 0], ref.mean(axis=(-2, -1))) <= TOL
+    assert floored_rel(f[:, 1], ref.std(axis=(-2, -1))) <= TOL
+    # channels are independent signals
+    f1, _ = plan.forward(torch.from_numpy(np.ascontiguousarray(x[:, 3:4])).cuda())
+    assert torch.equal(f1[0, 0], feats[0, 3])
+
+
 def test_max_order_1(wst):
     x = torch.rand(2, 1, 32, 32, device="cuda")
     p1, p2 = wst.get_plan(32, 32, 2, 8, 1), wst.get_plan(32, 32, 2, 8, 2)

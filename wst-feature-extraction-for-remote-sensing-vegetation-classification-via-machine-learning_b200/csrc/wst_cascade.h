@@ -36,11 +36,15 @@
 
 namespace wst {
 
+#ifndef WST_NT
+#define WST_NT 640
+#endif
 constexpr int kMaxJ = 6;
 constexpr int kMaxL = 8;                 // orientations per scale supported by the compiled cascades
 constexpr int kMaxPairs = kMaxJ * (kMaxJ - 1) / 2;
 WST_CX int pair_index(int j2, int j1) { return j2 * (j2 - 1) / 2 + j1; }
 constexpr int kSmemCfloats = 27000;      // data region budget (216,000 B) of the 227 KB a CTA may use
+constexpr int kGlobalCfloats = 1 << 24;  // data region budget of the global-workspace variant (128 MiB per CTA, never reached)
 
 // ------------------------------------------------------------------ 1-D factorisation n = R1*R2
 WST_CX int fft_R2(int n) {               // contiguous radix
@@ -54,6 +58,14 @@ WST_CX int fft_R2(int n) {               // contiguous radix
         long d = (long)r2 * r2 - n;      // distance of r2 from sqrt(n), in squared units
         if (d < 0) d = -d;
         if (d < best_score) { best_score = d; best = r2; }
+    }
+    if (best == 0) {                     // large sides (e.g. 576 = 24 x 24): any divisor pair with both radices <= 24
+        for (int r2 = 2; r2 <= 24; ++r2) {
+            if (n % r2 != 0 || n / r2 > 24) continue;
+            long d = (long)r2 * r2 - n;
+            if (d < 0) d = -d;
+            if (d < best_score) { best_score = d; best = r2; }
+        }
     }
     return best;
 }
@@ -69,9 +81,14 @@ template <int N> struct Fft1 {
 };
 
 // ------------------------------------------------------------------ geometry shared by host and device
-template <int N_, int J_, int NT_ = 512>
+// WS_GLOBAL = false: the data region lives in shared memory (the fast path, N <= 160).
+// WS_GLOBAL = true : same program, data region in a per-CTA global-memory workspace — correct for sides whose
+//                    spectra exceed one SM's shared memory (512x512 J=5 -> 576), not yet tuned.
+template <int N_, int J_, int NT_ = WST_NT, bool WS_GLOBAL_ = false>
 struct Cfg {
     static constexpr int N = N_, J = J_, NT = NT_;
+    static constexpr bool WS_GLOBAL = WS_GLOBAL_;
+    static constexpr int BUDGET = WS_GLOBAL_ ? kGlobalCfloats : kSmemCfloats;
     static constexpr int NS = N >> J;           // side of the subsampled (still padded) output grid
     static constexpr int HOUT = NS - 2;         // kept outputs per side after unpad [1:-1]
     static constexpr int HP = (HOUT + 3) & ~3;  // padded to float4
@@ -92,7 +109,7 @@ struct Cfg {
     static WST_CX int level_total(int j, int gp) {
         int m = msize(j);
         if (!has_children(j)) return gp * vsz(m);
-        int room = kSmemCfloats - gp * uhsz(m);
+        int room = BUDGET - gp * uhsz(m);
         if (room < zend(m, gp)) return 1 << 30;
         int offb = zend(m, gp);
         for (int j2 = j + 1; j2 < J; ++j2) {
@@ -105,11 +122,11 @@ struct Cfg {
     }
     // number of same-scale parents processed together at level j
     static WST_CX int GP(int j) {
-        for (int g = 8; g > 1; g /= 2) if (level_total(j, g) <= kSmemCfloats) return g;
+        for (int g = 8; g > 1; g /= 2) if (level_total(j, g) <= BUDGET) return g;
         return 1;
     }
     static WST_CX int G2(int j1, int j2) {   // children group size
-        return pick_group(msize(j2), kSmemCfloats - GP(j1) * uhsz(msize(j1)));
+        return pick_group(msize(j2), BUDGET - GP(j1) * uhsz(msize(j1)));
     }
     static WST_CX int OFFB(int j) {          // offset of the parents' half spectra
         int gp = GP(j), m = msize(j);
@@ -147,10 +164,13 @@ struct Cfg {
     }
     static constexpr int LP_SLOTS = 40;         // (array, row-chunk) partial maps held between the two reduce phases
     static WST_CX int lpbuf_floats() { return any_fused() ? LP_SLOTS * HOUT * HOUT : 0; }
+    // bytes of dynamic shared memory, and of per-CTA global workspace (0 for the shared-memory variant)
     static WST_CX size_t smem_bytes() {
-        return (size_t)(smem_cfloats() + tw_total) * sizeof(cfloat) + (size_t)(g_total + lpbuf_floats()) * sizeof(float);
+        return (size_t)((WS_GLOBAL ? 0 : smem_cfloats()) + tw_total) * sizeof(cfloat)
+               + (size_t)(g_total + lpbuf_floats()) * sizeof(float);
     }
-    static_assert(level_total(0, 1) <= kSmemCfloats, "padded size too large for the shared-memory cascade");
+    static WST_CX size_t workspace_cfloats() { return WS_GLOBAL ? (size_t)smem_cfloats() : 0; }
+    static_assert(level_total(0, 1) <= BUDGET, "padded size too large for the shared-memory cascade");
 };
 
 // ------------------------------------------------------------------ device-side plan tables

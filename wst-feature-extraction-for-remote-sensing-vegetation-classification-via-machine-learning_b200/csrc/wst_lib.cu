@@ -21,6 +21,7 @@
 
 #include "wst_tables.h"
 #include "wst_filters.h"
+#include "wst_ops.h"
 #include "../../include/wst2d.h"
 
 using namespace wst;
@@ -37,58 +38,6 @@ int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
         if (_e != cudaSuccess)                                                                  \
             return fail(WST2D_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));    \
     } while (0)
-
-// ------------------------------------------------------------------------------------------------
-// the fused cascade
-// ------------------------------------------------------------------------------------------------
-template <class C>
-__global__ void __launch_bounds__(C::NT, 1)
-cascade_kernel(const PlanTables pt, const float* __restrict__ x, long long nsig, cfloat* u0h_scratch,
-               float* maps) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    cfloat* sm = reinterpret_cast<cfloat*>(smem_raw);
-    cfloat* twsm = sm + C::smem_cfloats();
-    float* gsm = reinterpret_cast<float*>(twsm + C::tw_total);
-    float* lpbuf = gsm + C::g_total;
-    DevExec ex;
-    const size_t sig_elems = (size_t)pt.H * pt.W;
-    const size_t map_elems = (size_t)pt.K * C::HOUT * C::HOUT;
-    Cascade<C, DevExec> prog{ex, pt, sm, twsm, gsm, lpbuf,
-                             u0h_scratch + (size_t)blockIdx.x * (C::N * (C::N / 2 + 1)), nullptr};
-    prog.load_twiddles();
-    for (long long s = blockIdx.x; s < nsig; s += gridDim.x) {
-        prog.maps = maps + (size_t)s * map_elems;
-        prog.run(x + (size_t)s * sig_elems);
-    }
-}
-
-// Debug twin of cascade_kernel: same program, executor that accumulates clock64() per phase tag.
-// CTA 0's totals (over the signals it processed) are written to `cycles`.
-template <class C>
-__global__ void __launch_bounds__(C::NT, 1)
-cascade_prof_kernel(const PlanTables pt, const float* __restrict__ x, long long nsig, cfloat* u0h_scratch,
-                    float* maps, long long* cycles) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ long long acc[kNumPhaseTags];
-    cfloat* sm = reinterpret_cast<cfloat*>(smem_raw);
-    cfloat* twsm = sm + C::smem_cfloats();
-    float* gsm = reinterpret_cast<float*>(twsm + C::tw_total);
-    float* lpbuf = gsm + C::g_total;
-    for (int i = threadIdx.x; i < kNumPhaseTags; i += C::NT) acc[i] = 0;
-    __syncthreads();
-    ProfExec ex{acc};
-    const size_t sig_elems = (size_t)pt.H * pt.W;
-    const size_t map_elems = (size_t)pt.K * C::HOUT * C::HOUT;
-    Cascade<C, ProfExec> prog{ex, pt, sm, twsm, gsm, lpbuf,
-                              u0h_scratch + (size_t)blockIdx.x * (C::N * (C::N / 2 + 1)), nullptr};
-    prog.load_twiddles();
-    for (long long s = blockIdx.x; s < nsig; s += gridDim.x) {
-        prog.maps = maps + (size_t)s * map_elems;
-        prog.run(x + (size_t)s * sig_elems);
-    }
-    if (blockIdx.x == 0)
-        for (int i = threadIdx.x; i < kNumPhaseTags; i += C::NT) cycles[i] = acc[i];
-}
 
 // ------------------------------------------------------------------------------------------------
 // pooling: one warp per coefficient map
@@ -202,56 +151,16 @@ __global__ void combine_filters_kernel(const double2* __restrict__ spec, int nwa
 // ------------------------------------------------------------------------------------------------
 // configuration dispatch
 // ------------------------------------------------------------------------------------------------
-struct CfgOps {
-    int N, J, NT, hout;
-    size_t smem;
-    const void* kernel;
-    bool (*build)(int, const float*, const float*, std::vector<float>&, TableOffsets&, std::string&);
-    void (*bind)(PlanTables&, const float*, const TableOffsets&);
-    cudaError_t (*launch)(const PlanTables&, const float*, long long, cfloat*, float*, int, cudaStream_t);
-    cudaError_t (*launch_prof)(const PlanTables&, const float*, long long, cfloat*, float*, long long*, int, cudaStream_t);
-};
-
-template <class C>
-cudaError_t launch_cascade(const PlanTables& pt, const float* x, long long nsig, cfloat* u0h, float* maps,
-                           int grid, cudaStream_t st) {
-    cascade_kernel<C><<<grid, C::NT, C::smem_bytes(), st>>>(pt, x, nsig, u0h, maps);
-    return cudaGetLastError();
-}
-
-template <class C>
-cudaError_t launch_cascade_prof(const PlanTables& pt, const float* x, long long nsig, cfloat* u0h, float* maps,
-                                long long* cycles, int grid, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(cascade_prof_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)C::smem_bytes());
-    if (e != cudaSuccess) return e;
-    cascade_prof_kernel<C><<<grid, C::NT, C::smem_bytes(), st>>>(pt, x, nsig, u0h, maps, cycles);
-    return cudaGetLastError();
-}
-
-template <class C>
-CfgOps make_ops() {
-    static_assert(C::smem_bytes() + kNumPhaseTags * 8 <= 232448, "configuration exceeds the 227 KB of shared memory a CTA may use");
-    CfgOps o;
-    o.N = C::N; o.J = C::J; o.NT = C::NT; o.hout = C::HOUT;
-    o.smem = C::smem_bytes();
-    o.kernel = (const void*)cascade_kernel<C>;
-    o.build = &build_tables<C>;
-    o.bind = &bind_tables<C>;
-    o.launch = &launch_cascade<C>;
-    o.launch_prof = &launch_cascade_prof<C>;
-    return o;
-}
-
 const std::vector<CfgOps>& all_ops() {
     static const std::vector<CfgOps> ops = {
-#define CFG(n, j) make_ops<Cfg<n, j>>(),
+#define CFG(n, j) wst_make_ops_##n##_##j(),
+#define CFGG(n, j) wst_make_ops_##n##_##j(),
 #include "wst_configs.inc"
 #undef CFG
+#undef CFGG
     };
     return ops;
 }
-
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -278,6 +187,7 @@ struct wst2d_plan {
         float* x[2] = {nullptr, nullptr};
         float* f[2] = {nullptr, nullptr};
         cfloat* u0h[2] = {nullptr, nullptr};
+        cfloat* ws[2] = {nullptr, nullptr};
         float* maps[2] = {nullptr, nullptr};
         long long cap_sig = 0;        // signals per chunk the buffers are sized for
     };
@@ -370,18 +280,28 @@ long long chunk_signals(const wst2d_plan* p, long long nsig) {
 // own_u0h / own_maps: caller-provided scratch (host path) sized for grid_max CTAs / nsig signals; when NULL
 // the scratch is stream-ordered (cudaMallocAsync from the device's default pool).
 int forward_impl(const wst2d_plan* p, const float* x_dev, long long nsig, float* feats_dev,
-                 float* maps_dev, cudaStream_t st, cfloat* own_u0h = nullptr, float* own_maps = nullptr) {
+                 float* maps_dev, cudaStream_t st, cfloat* own_u0h = nullptr, float* own_maps = nullptr,
+                 cfloat* own_ws = nullptr) {
     if (nsig == 0) return WST2D_OK;
     const size_t sig_elems = (size_t)p->H * p->W;
     const size_t map_elems = (size_t)p->K * p->hout * p->hout;
     const size_t u0h_elems = (size_t)p->N * (p->N / 2 + 1);
     const long long chunk = (maps_dev || own_maps) ? nsig : chunk_signals(p, nsig);
     const int grid_all = (int)(nsig < p->grid_max ? nsig : p->grid_max);
-    cfloat* d_u0h = own_u0h; float* d_maps = own_maps;
+    cfloat* d_u0h = own_u0h; float* d_maps = own_maps; cfloat* d_ws = own_ws;
+    const size_t ws_elems = p->ops->workspace_cfloats;
     if (!own_u0h) CUDA_TRY(cudaMallocAsync(&d_u0h, (size_t)grid_all * u0h_elems * sizeof(cfloat), st));
+    if (ws_elems && !own_ws) {
+        cudaError_t e = cudaMallocAsync(&d_ws, (size_t)grid_all * ws_elems * sizeof(cfloat), st);
+        if (e != cudaSuccess) { if (!own_u0h) cudaFreeAsync(d_u0h, st); return fail(WST2D_ERR_CUDA, std::string("cudaMallocAsync(workspace): ") + cudaGetErrorString(e)); }
+    }
     if (!maps_dev && !own_maps) {
         cudaError_t e = cudaMallocAsync(&d_maps, (size_t)chunk * map_elems * sizeof(float), st);
-        if (e != cudaSuccess) { cudaFreeAsync(d_u0h, st); return fail(WST2D_ERR_CUDA, std::string("cudaMallocAsync(maps): ") + cudaGetErrorString(e)); }
+        if (e != cudaSuccess) {
+            if (!own_u0h) cudaFreeAsync(d_u0h, st);
+            if (ws_elems && !own_ws) cudaFreeAsync(d_ws, st);
+            return fail(WST2D_ERR_CUDA, std::string("cudaMallocAsync(maps): ") + cudaGetErrorString(e));
+        }
     }
     int rc = WST2D_OK;
     for (long long s0 = 0; s0 < nsig && rc == WST2D_OK; s0 += chunk) {
@@ -389,7 +309,7 @@ int forward_impl(const wst2d_plan* p, const float* x_dev, long long nsig, float*
         int grid = (int)(n < p->grid_max ? n : p->grid_max);
         float* maps = maps_dev ? maps_dev + (size_t)s0 * map_elems : d_maps;
         prof_mark(p, p->prof_cascade, st);
-        cudaError_t e = p->ops->launch(p->pt, x_dev + (size_t)s0 * sig_elems, n, d_u0h, maps, grid, st);
+        cudaError_t e = p->ops->launch(p->pt, x_dev + (size_t)s0 * sig_elems, n, d_u0h, d_ws, maps, grid, st);
         prof_mark(p, p->prof_cascade, st);
         if (e != cudaSuccess) { rc = fail(WST2D_ERR_CUDA, std::string("cascade launch: ") + cudaGetErrorString(e)); break; }
         if (feats_dev) {
@@ -405,6 +325,7 @@ int forward_impl(const wst2d_plan* p, const float* x_dev, long long nsig, float*
         }
     }
     if (!own_u0h) cudaFreeAsync(d_u0h, st);
+    if (ws_elems && !own_ws) cudaFreeAsync(d_ws, st);
     if (d_maps && !own_maps) cudaFreeAsync(d_maps, st);
     return rc;
 }
@@ -486,6 +407,7 @@ int wst2d_plan_destroy(wst2d_plan* plan) {
     for (int i = 0; i < 2; ++i) {
         if (plan->host.st[i]) { cudaStreamSynchronize(plan->host.st[i]); cudaStreamDestroy(plan->host.st[i]); }
         cudaFree(plan->host.x[i]); cudaFree(plan->host.f[i]); cudaFree(plan->host.u0h[i]); cudaFree(plan->host.maps[i]);
+        cudaFree(plan->host.ws[i]);
     }
     cudaFree(plan->d_tables);
     delete plan;
@@ -552,8 +474,8 @@ int wst2d_forward_host(const wst2d_plan* p, const float* x_host, int64_t B, int 
     if (hp.cap_sig < chunk_sig) {           // (re)size the cached staging buffers; first call or larger C
         for (int i = 0; i < 2; ++i) {
             if (hp.st[i]) cudaStreamSynchronize(hp.st[i]);
-            cudaFree(hp.x[i]); cudaFree(hp.f[i]); cudaFree(hp.u0h[i]); cudaFree(hp.maps[i]);
-            hp.x[i] = hp.f[i] = hp.maps[i] = nullptr; hp.u0h[i] = nullptr;
+            cudaFree(hp.x[i]); cudaFree(hp.f[i]); cudaFree(hp.u0h[i]); cudaFree(hp.maps[i]); cudaFree(hp.ws[i]);
+            hp.x[i] = hp.f[i] = hp.maps[i] = nullptr; hp.u0h[i] = nullptr; hp.ws[i] = nullptr;
         }
         hp.cap_sig = 0;
         for (int i = 0; i < 2; ++i) {
@@ -562,6 +484,8 @@ int wst2d_forward_host(const wst2d_plan* p, const float* x_host, int64_t B, int 
             CUDA_TRY(cudaMalloc(&hp.f[i], chunk_sig * sig_out * sizeof(float)));
             CUDA_TRY(cudaMalloc(&hp.u0h[i], (size_t)p->grid_max * p->N * (p->N / 2 + 1) * sizeof(cfloat)));
             CUDA_TRY(cudaMalloc(&hp.maps[i], chunk_sig * map_elems * sizeof(float)));
+            if (p->ops->workspace_cfloats)
+                CUDA_TRY(cudaMalloc(&hp.ws[i], (size_t)p->grid_max * p->ops->workspace_cfloats * sizeof(cfloat)));
         }
         hp.cap_sig = chunk_sig;
     }
@@ -573,7 +497,7 @@ int wst2d_forward_host(const wst2d_plan* p, const float* x_host, int64_t B, int 
         cudaError_t e = cudaMemcpyAsync(hp.x[i], x_host + (size_t)s0 * sig_in, n * sig_in * sizeof(float),
                                         cudaMemcpyHostToDevice, hp.st[i]);
         if (e != cudaSuccess) { rc = fail(WST2D_ERR_CUDA, std::string("H2D: ") + cudaGetErrorString(e)); break; }
-        rc = forward_impl(p, hp.x[i], n, hp.f[i], nullptr, hp.st[i], hp.u0h[i], hp.maps[i]);
+        rc = forward_impl(p, hp.x[i], n, hp.f[i], nullptr, hp.st[i], hp.u0h[i], hp.maps[i], hp.ws[i]);
         if (rc != WST2D_OK) break;
         e = cudaMemcpyAsync(feats_host + (size_t)s0 * sig_out, hp.f[i], n * sig_out * sizeof(float),
                             cudaMemcpyDeviceToHost, hp.st[i]);
@@ -658,14 +582,15 @@ int wst2d_debug_phase_cycles(const wst2d_plan* p, const float* x_dev, int64_t ns
     if (nsig <= 0) return fail(WST2D_ERR_ARG, "nsig must be positive");
     DeviceGuard guard(p->device);
     const int grid = (int)(nsig < p->grid_max ? nsig : p->grid_max);
-    cfloat* d_u0h = nullptr; float* d_maps = nullptr; long long* d_cyc = nullptr;
+    cfloat* d_u0h = nullptr; float* d_maps = nullptr; long long* d_cyc = nullptr; cfloat* d_ws = nullptr;
     CUDA_TRY(cudaMalloc(&d_u0h, (size_t)grid * p->N * (p->N / 2 + 1) * sizeof(cfloat)));
+    if (p->ops->workspace_cfloats) CUDA_TRY(cudaMalloc(&d_ws, (size_t)grid * p->ops->workspace_cfloats * sizeof(cfloat)));
     CUDA_TRY(cudaMalloc(&d_maps, (size_t)nsig * p->K * p->hout * p->hout * sizeof(float)));
     CUDA_TRY(cudaMalloc(&d_cyc, kNumPhaseTags * sizeof(long long)));
-    cudaError_t e = p->ops->launch_prof(p->pt, x_dev, nsig, d_u0h, d_maps, d_cyc, grid, nullptr);
+    cudaError_t e = p->ops->launch_prof(p->pt, x_dev, nsig, d_u0h, d_ws, d_maps, d_cyc, grid, nullptr);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e == cudaSuccess) e = cudaMemcpy(cycles_host, d_cyc, kNumPhaseTags * sizeof(long long), cudaMemcpyDeviceToHost);
-    cudaFree(d_u0h); cudaFree(d_maps); cudaFree(d_cyc);
+    cudaFree(d_u0h); cudaFree(d_maps); cudaFree(d_cyc); cudaFree(d_ws);
     if (e != cudaSuccess) return fail(WST2D_ERR_CUDA, std::string("phase profile: ") + cudaGetErrorString(e));
     return WST2D_OK;
 }

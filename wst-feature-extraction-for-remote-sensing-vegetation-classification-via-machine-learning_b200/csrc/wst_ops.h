@@ -1,0 +1,29 @@
+// wst_ops.h — the per-configuration entry points wst_lib.cu dispatches on.  Each compiled (N, J) lives in its
+// own translation unit (wst_cfg_inst.cu compiled with -DWST_CFG_N=.. -DWST_CFG_J=..), so configurations build
+// in parallel.
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include "wst_tables.h"
+
+namespace wst {
+
+struct CfgOps {
+    int N, J, NT, hout;
+    size_t smem;                 // dynamic shared memory per CTA
+    size_t workspace_cfloats;    // per-CTA global workspace (0: data region in shared memory)
+    const void* kernel;
+    bool (*build)(int, const float*, const float*, std::vector<float>&, TableOffsets&, std::string&);
+    void (*bind)(PlanTables&, const float*, const TableOffsets&);
+    cudaError_t (*launch)(const PlanTables&, const float*, long long, cfloat*, cfloat*, float*, int, cudaStream_t);
+    cudaError_t (*launch_prof)(const PlanTables&, const float*, long long, cfloat*, cfloat*, float*, long long*, int, cudaStream_t);
+};
+
+}  // namespace wst
+
+#define CFG(n, j) wst::CfgOps wst_make_ops_##n##_##j();
+#define CFGG(n, j) wst::CfgOps wst_make_ops_##n##_##j();
+#include "wst_configs.inc"
+#undef CFG
+#undef CFGG
