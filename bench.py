@@ -317,7 +317,6 @@ def run_ours(args, cfg):
                          "frac": round(achieved / hbm_peak, 6), "traffic": traffic, "peak_source": peak_src,
                          "kernel": "cascade_kernel", "kernel_ms_per_launch": round(avg_launch_ms, 4),
                          "kernel_share_of_step": round(cas_ms / ms, 4) if ms else None,
-                         "pool_kernel_share_of_step": round(pool_ms / ms, 4) if ms else None,
                          "algorithmic_bytes_per_patch": bytes_min,
                          "note": "fused path is fp32/shared-memory bound (SURVEY.md F3); see fp32"},
             "fp32": {"model_flops_per_patch": fl, "achieved_tflops": round(value / world * fl / 1e12, 3),

@@ -72,7 +72,9 @@ int wst2d_forward_host(const wst2d_plan* plan, const float* x_host, int64_t B, i
  * psi_hat [J*L][Hp][Wp], phi_hat [Hp][Wp]; either may be NULL. */
 int wst2d_plan_filters(const wst2d_plan* plan, float* psi_hat, float* phi_hat);
 
-/* Number of kernels wst2d_forward launches for a batch of B*C signals (for launch accounting). */
+/* Number of kernels wst2d_forward launches for a batch of B*C signals (for launch accounting): the cascade
+ * kernel pools in-kernel, so this is 1 (wst2d_forward_u8 adds its conversion kernel, wst2d_forward_host
+ * launches one per chunk). */
 int wst2d_launch_count(const wst2d_plan* plan, int64_t B, int C);
 
 /* Optional per-kernel timing for bench.py's roofline: when enabled, wst2d_forward records CUDA events

@@ -29,7 +29,7 @@ def load():
         lib = ctypes.CDLL(LIB)
         lib.emu_last_error.restype = ctypes.c_char_p
         lib.emu_fft2.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
-        lib.emu_forward.argtypes = [ctypes.c_int] * 6 + [ctypes.c_void_p] * 3 + [ctypes.c_int, ctypes.c_void_p]
+        lib.emu_forward.argtypes = [ctypes.c_int] * 6 + [ctypes.c_void_p] * 3 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         lib.emu_filter_bank.argtypes = [ctypes.c_int] * 3 + [ctypes.c_void_p] * 2
         lib.emu_query.argtypes = [ctypes.c_int, ctypes.c_int] + [ctypes.POINTER(ctypes.c_int)] * 3
         _lib = lib
@@ -54,8 +54,9 @@ def filter_bank(N, J, L):
     return psi, phi
 
 
-def forward(x, J, L, max_order, psi_hat, phi_hat):
-    """Replay the cascade kernel for signals x [nsig, H, W]; returns maps [nsig, K, h, h]."""
+def forward(x, J, L, max_order, psi_hat, phi_hat, with_features=False):
+    """Replay the cascade kernel for signals x [nsig, H, W]; returns maps [nsig, K, h, h]
+    (and the in-kernel pooled features [nsig, 2, K] when with_features)."""
     x = np.ascontiguousarray(x, np.float32)
     nsig, H, W = x.shape
     N = psi_hat.shape[-1]
@@ -64,8 +65,9 @@ def forward(x, J, L, max_order, psi_hat, phi_hat):
     out = np.full((nsig, K, h, h), np.nan, np.float32)
     psi_hat = np.ascontiguousarray(psi_hat, np.float32)
     phi_hat = np.ascontiguousarray(phi_hat, np.float32)
+    feats = np.full((nsig, 2, K), np.nan, np.float32) if with_features else None
     rc = load().emu_forward(N, J, L, max_order, H, W, psi_hat.ctypes.data, phi_hat.ctypes.data,
-                            x.ctypes.data, nsig, out.ctypes.data)
+                            x.ctypes.data, nsig, out.ctypes.data, feats.ctypes.data if with_features else None)
     if rc != 0:
         raise RuntimeError(load().emu_last_error().decode())
-    return out
+    return (out, feats) if with_features else out

@@ -19,7 +19,7 @@ namespace {
 
 template <class C>
 int run_cfg(int L, int max_order, int H, int W, const float* psi_hat, const float* phi_hat,
-            const float* x, int nsig, float* maps_out, std::string& err) {
+            const float* x, int nsig, float* maps_out, float* feats_out, std::string& err) {
     std::vector<float> buf; TableOffsets off;
     if (!build_tables<C>(L, psi_hat, phi_hat, buf, off, err)) return -1;
     PlanTables pt{};
@@ -37,7 +37,7 @@ int run_cfg(int L, int max_order, int H, int W, const float* psi_hat, const floa
         for (auto& v : lpbuf) v = NAN;
         Cascade<C, HostExec<C::NT>> prog{ex, pt, sm.data(), twsm.data(), gsm.data(), lpbuf.data(), u0h.data(), maps_out + s * map_sz};
         prog.load_twiddles();
-        prog.run(x + (size_t)s * H * W);
+        prog.run(x + (size_t)s * H * W, feats_out ? feats_out + (size_t)s * 2 * pt.K : nullptr);
     }
     return 0;
 }
@@ -87,11 +87,11 @@ int emu_fft2(int M, int dir, float* data) {
     return -2;
 }
 
-// Full cascade for nsig signals of H x W; writes maps [nsig][K][HOUT][HOUT].
+// Full cascade for nsig signals of H x W; writes maps [nsig][K][HOUT][HOUT] and (if non-NULL) feats [nsig][2][K].
 int emu_forward(int N, int J, int L, int max_order, int H, int W, const float* psi_hat,
-                const float* phi_hat, const float* x, int nsig, float* maps_out) {
-#define CFG(n, j) if (N == n && J == j) return run_cfg<Cfg<n, j>>(L, max_order, H, W, psi_hat, phi_hat, x, nsig, maps_out, g_err);
-#define CFGG(n, j) if (N == n && J == j) return run_cfg<Cfg<n, j, 256, true>>(L, max_order, H, W, psi_hat, phi_hat, x, nsig, maps_out, g_err);
+                const float* phi_hat, const float* x, int nsig, float* maps_out, float* feats_out) {
+#define CFG(n, j) if (N == n && J == j) return run_cfg<Cfg<n, j>>(L, max_order, H, W, psi_hat, phi_hat, x, nsig, maps_out, feats_out, g_err);
+#define CFGG(n, j) if (N == n && J == j) return run_cfg<Cfg<n, j, 256, true>>(L, max_order, H, W, psi_hat, phi_hat, x, nsig, maps_out, feats_out, g_err);
 #include "wst_configs.inc"
 #undef CFG
 #undef CFGG

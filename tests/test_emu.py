@@ -33,12 +33,16 @@ def test_filter_bank_formula(N, J, L):
     assert np.abs(phi - fb["phi"]["levels"][0]).max() < 1e-6
 
 
-@pytest.mark.parametrize("M,J,L,mo", [(32, 2, 8, 2), (32, 2, 8, 1), (32, 3, 6, 2), (64, 3, 8, 2)])
+@pytest.mark.parametrize("M,J,L,mo", [(32, 2, 8, 2), (32, 2, 8, 1), (32, 3, 6, 2), (64, 3, 8, 2), (128, 2, 8, 2)])
 def test_cascade_vs_oracle(M, J, L, mo):
     rng = np.random.default_rng(7)
     x = (rng.integers(0, 256, (2, M, M)) / 255.0).astype(np.float32)
     S = Scattering2D(J=J, shape=(M, M), L=L, max_order=mo, precision="double", cache_filters=True)
     psi = np.stack([p["levels"][0] for p in S.psi]); phi = S.phi["levels"][0]
-    got = emu.forward(x, J, L, mo, psi, phi)
-    assert not np.isnan(got).any()
-    assert floored_rel(got, S(x)) <= 1e-4 / 4
+    got, feats = emu.forward(x, J, L, mo, psi, phi, with_features=True)
+    assert not np.isnan(got).any() and not np.isnan(feats).any()
+    ref = S(x)
+    assert floored_rel(got, ref) <= 1e-4 / 4
+    assert floored_rel(feats[:, 0], ref.mean(axis=(-2, -1))) <= 1e-4 / 4       # in-kernel pooling
+    tau = 1e-3 * np.abs(ref.mean(axis=(-2, -1))).max(axis=1, keepdims=True)
+    assert float((np.abs(feats[:, 1] - ref.std(axis=(-2, -1))) / np.maximum(ref.std(axis=(-2, -1)), tau)).max()) <= 1e-4 / 4

@@ -195,7 +195,7 @@ constexpr float kSupportEps = 1e-7f;
 // executor of the debug entry point; the production executor ignores them.
 enum PhaseKind { PK_TWIDDLE = 0, PK_INPUT, PK_LP1, PK_LP2, PK_RFFT_ROW_S, PK_RFFT_ROW_C, PK_RFFT_SPLIT,
                  PK_RFFT_COL_S, PK_RFFT_COL_C, PK_U0_STORE, PK_PROD1, PK_PROD2, PK_IFFT_COL_C, PK_IFFT_COL_S,
-                 PK_IFFT_ROW_C, PK_IFFT_FINAL, PK_LPR, PK_LPS, PK_COUNT };
+                 PK_IFFT_ROW_C, PK_IFFT_FINAL, PK_LPR, PK_LPS, PK_POOL, PK_COUNT };
 constexpr int kNumPhaseTags = PK_COUNT * 8;
 
 #ifdef __CUDACC__
@@ -749,9 +749,54 @@ struct Cascade {
         }
     }
 
-    WST_D void run(const float* x) {
+    // Per-coefficient mean and population std over the h x w map (np.mean / np.std of
+    // train_and_save_model.py:371-372), two-pass, from the maps this CTA has just written:
+    //   feats[0][k] = mean, feats[1][k] = std.
+    WST_D void pool(float* feats) {
+        constexpr int NPIX = HOUT * HOUT;
+        const int K = pt.K;
+        int parts = 1;
+        while (parts < 8 && K * parts * 2 <= NT && NPIX / (parts * 2) >= 16) parts *= 2;
+        const int slice = NPIX / parts;                      // NPIX is a multiple of 4, parts a power of two <= 8
+        float* scr = reinterpret_cast<float*>(sm);           // the data region is free at the end of a signal
+        ex.template phase<PK_POOL * 8>([&](int tid) {
+            for (int o = tid; o < K * parts; o += NT) {
+                const float4* p = reinterpret_cast<const float4*>(maps + (size_t)(o / parts) * NPIX + (o % parts) * slice);
+                float sacc = 0.f;
+                for (int i = 0; i < slice / 4; ++i) { float4 v = p[i]; sacc += (v.x + v.y) + (v.z + v.w); }
+                scr[o] = sacc;
+            }
+        });
+        ex.template phase<PK_POOL * 8 + 1>([&](int tid) {
+            for (int o = tid; o < K * parts; o += NT) {
+                const int k = o / parts;
+                float tot = 0.f;
+                for (int q = 0; q < parts; ++q) tot += scr[k * parts + q];
+                const float mean = tot * (1.0f / NPIX);
+                const float4* p = reinterpret_cast<const float4*>(maps + (size_t)k * NPIX + (o % parts) * slice);
+                float vacc = 0.f;
+                for (int i = 0; i < slice / 4; ++i) {
+                    float4 v = p[i];
+                    float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+                    vacc += (a * a + b * b) + (c * c + d * d);
+                }
+                scr[K * parts + o] = vacc;
+            }
+        });
+        ex.template phase<PK_POOL * 8 + 2>([&](int tid) {
+            for (int k = tid; k < K; k += NT) {
+                float tot = 0.f, var = 0.f;
+                for (int q = 0; q < parts; ++q) { tot += scr[k * parts + q]; var += scr[K * parts + k * parts + q]; }
+                feats[k] = tot * (1.0f / NPIX);
+                feats[K + k] = sqrtf(var * (1.0f / NPIX));
+            }
+        });
+    }
+
+    WST_D void run(const float* x, float* feats) {
         input_stage(x);
         static_for<0, J>([&](auto Jc) { this->template level<decltype(Jc)::value>(); });
+        if (feats) pool(feats);
     }
 };
 

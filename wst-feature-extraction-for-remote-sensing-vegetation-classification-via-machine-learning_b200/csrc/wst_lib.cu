@@ -1,11 +1,10 @@
 // wst_lib.cu — CUDA kernels (sm_100a) and the C ABI of libwst_b200.so (include/wst2d.h).
 //
 // Kernels:
-//   cascade_kernel<Cfg>   one persistent CTA per SM; each CTA runs the whole scattering cascade of
-//                         one (patch, channel) signal at a time out of shared memory (wst_cascade.h)
-//   pool_kernel           per-coefficient mean / population std over the h x w map, one warp per
-//                         map, warp-shuffle reductions (np.mean / np.std of
-//                         train_and_save_model.py:371-372)
+//   cascade_kernel<Cfg>   (wst_cfg_inst.cu, one translation unit per configuration) one persistent CTA per
+//                         SM; each CTA runs the whole scattering cascade of one (patch, channel) signal at a
+//                         time out of shared memory and pools its maps (mean / population std,
+//                         train_and_save_model.py:371-372) before moving on (wst_cascade.h)
 //   u8_to_chw_kernel      uint8 HWC -> float32 CHW / 255 (load_rgb_image, train...:51-56)
 //   gabor_spatial_kernel, dft_axis{0,1}_kernel, combine_filters_kernel
 //                         fp64 filter-bank construction, once per plan (wst_filters.h)
@@ -38,34 +37,6 @@ int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
         if (_e != cudaSuccess)                                                                  \
             return fail(WST2D_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));    \
     } while (0)
-
-// ------------------------------------------------------------------------------------------------
-// pooling: one warp per coefficient map
-// ------------------------------------------------------------------------------------------------
-__global__ void pool_kernel(const float* __restrict__ maps, float* __restrict__ feats,
-                            long long nsig, int K, int npix) {
-    const int lane = threadIdx.x & 31;
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const float inv = 1.0f / (float)npix;
-    for (long long m = warp; m < nsig * K; m += nwarps) {
-        const float* p = maps + (size_t)m * npix;
-        float s = 0.f;
-        for (int i = lane; i < npix; i += 32) s += p[i];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        const float mean = s * inv;
-        float v = 0.f;
-        for (int i = lane; i < npix; i += 32) { float d = p[i] - mean; v = fmaf(d, d, v); }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) {
-            long long sig = m / K; int k = (int)(m - sig * K);
-            feats[(size_t)sig * 2 * K + k] = mean;
-            feats[(size_t)sig * 2 * K + K + k] = sqrtf(v * inv);
-        }
-    }
-}
 
 // uint8 [B][H][W][C] -> float32 [B][C][H][W] / 255
 __global__ void u8_to_chw_kernel(const uint8_t* __restrict__ in, float* __restrict__ out,
@@ -264,69 +235,35 @@ __global__ void fma_peak_kernel(float* out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
-// Signals per cascade launch when the maps go to the internal scratch: the scratch is bounded to
-// ~1 GiB, and the chunks are balanced and rounded to whole persistent-grid waves.
-long long chunk_signals(const wst2d_plan* p, long long nsig) {
-    size_t map_bytes = (size_t)p->K * p->hout * p->hout * sizeof(float);
-    long long cmax = (long long)((size_t)1 << 30) / (long long)map_bytes;
-    if (cmax < p->grid_max) cmax = p->grid_max;
-    if (nsig <= cmax) return nsig;
-    long long nch = (nsig + cmax - 1) / cmax;
-    long long c = (nsig + nch - 1) / nch;
-    c = (c + p->grid_max - 1) / p->grid_max * p->grid_max;
-    return c;
-}
-
-// own_u0h / own_maps: caller-provided scratch (host path) sized for grid_max CTAs / nsig signals; when NULL
-// the scratch is stream-ordered (cudaMallocAsync from the device's default pool).
+// One cascade launch over nsig signals.  The kernel pools each signal's maps itself; when the caller does not
+// want the maps they live in a per-CTA scratch (grid x K*h*w floats, L2-resident) instead of HBM.
+// own_*: caller-provided scratch (host path) sized for grid_max CTAs; when NULL the scratch is stream-ordered
+// (cudaMallocAsync from the device's default pool).
 int forward_impl(const wst2d_plan* p, const float* x_dev, long long nsig, float* feats_dev,
                  float* maps_dev, cudaStream_t st, cfloat* own_u0h = nullptr, float* own_maps = nullptr,
                  cfloat* own_ws = nullptr) {
     if (nsig == 0) return WST2D_OK;
-    const size_t sig_elems = (size_t)p->H * p->W;
     const size_t map_elems = (size_t)p->K * p->hout * p->hout;
     const size_t u0h_elems = (size_t)p->N * (p->N / 2 + 1);
-    const long long chunk = (maps_dev || own_maps) ? nsig : chunk_signals(p, nsig);
-    const int grid_all = (int)(nsig < p->grid_max ? nsig : p->grid_max);
-    cfloat* d_u0h = own_u0h; float* d_maps = own_maps; cfloat* d_ws = own_ws;
     const size_t ws_elems = p->ops->workspace_cfloats;
-    if (!own_u0h) CUDA_TRY(cudaMallocAsync(&d_u0h, (size_t)grid_all * u0h_elems * sizeof(cfloat), st));
-    if (ws_elems && !own_ws) {
-        cudaError_t e = cudaMallocAsync(&d_ws, (size_t)grid_all * ws_elems * sizeof(cfloat), st);
-        if (e != cudaSuccess) { if (!own_u0h) cudaFreeAsync(d_u0h, st); return fail(WST2D_ERR_CUDA, std::string("cudaMallocAsync(workspace): ") + cudaGetErrorString(e)); }
-    }
-    if (!maps_dev && !own_maps) {
-        cudaError_t e = cudaMallocAsync(&d_maps, (size_t)chunk * map_elems * sizeof(float), st);
-        if (e != cudaSuccess) {
-            if (!own_u0h) cudaFreeAsync(d_u0h, st);
-            if (ws_elems && !own_ws) cudaFreeAsync(d_ws, st);
-            return fail(WST2D_ERR_CUDA, std::string("cudaMallocAsync(maps): ") + cudaGetErrorString(e));
-        }
-    }
+    const int grid = (int)(nsig < p->grid_max ? nsig : p->grid_max);
+    cfloat* d_u0h = own_u0h; float* d_maps = own_maps; cfloat* d_ws = own_ws;
+    cudaError_t e = cudaSuccess;
+    if (!d_u0h) e = cudaMallocAsync(&d_u0h, (size_t)grid * u0h_elems * sizeof(cfloat), st);
+    if (e == cudaSuccess && ws_elems && !d_ws) e = cudaMallocAsync(&d_ws, (size_t)grid * ws_elems * sizeof(cfloat), st);
+    if (e == cudaSuccess && !maps_dev && !d_maps) e = cudaMallocAsync(&d_maps, (size_t)grid * map_elems * sizeof(float), st);
     int rc = WST2D_OK;
-    for (long long s0 = 0; s0 < nsig && rc == WST2D_OK; s0 += chunk) {
-        long long n = nsig - s0 < chunk ? nsig - s0 : chunk;
-        int grid = (int)(n < p->grid_max ? n : p->grid_max);
-        float* maps = maps_dev ? maps_dev + (size_t)s0 * map_elems : d_maps;
+    if (e != cudaSuccess) {
+        rc = fail(WST2D_ERR_CUDA, std::string("cudaMallocAsync(scratch): ") + cudaGetErrorString(e));
+    } else {
         prof_mark(p, p->prof_cascade, st);
-        cudaError_t e = p->ops->launch(p->pt, x_dev + (size_t)s0 * sig_elems, n, d_u0h, d_ws, maps, grid, st);
+        e = p->ops->launch(p->pt, x_dev, nsig, d_u0h, d_ws, maps_dev, maps_dev ? nullptr : d_maps, feats_dev, grid, st);
         prof_mark(p, p->prof_cascade, st);
-        if (e != cudaSuccess) { rc = fail(WST2D_ERR_CUDA, std::string("cascade launch: ") + cudaGetErrorString(e)); break; }
-        if (feats_dev) {
-            long long nmaps = n * p->K;
-            long long blocks = (nmaps + 7) / 8;                 // 8 warps per block
-            if (blocks > 148 * 16) blocks = 148 * 16;
-            prof_mark(p, p->prof_pool, st);
-            pool_kernel<<<(unsigned)blocks, 256, 0, st>>>(maps, feats_dev + (size_t)s0 * 2 * p->K, n, p->K,
-                                                          p->hout * p->hout);
-            prof_mark(p, p->prof_pool, st);
-            e = cudaGetLastError();
-            if (e != cudaSuccess) { rc = fail(WST2D_ERR_CUDA, std::string("pool launch: ") + cudaGetErrorString(e)); break; }
-        }
+        if (e != cudaSuccess) rc = fail(WST2D_ERR_CUDA, std::string("cascade launch: ") + cudaGetErrorString(e));
     }
-    if (!own_u0h) cudaFreeAsync(d_u0h, st);
-    if (ws_elems && !own_ws) cudaFreeAsync(d_ws, st);
-    if (d_maps && !own_maps) cudaFreeAsync(d_maps, st);
+    if (!own_u0h && d_u0h) cudaFreeAsync(d_u0h, st);
+    if (!own_ws && d_ws) cudaFreeAsync(d_ws, st);
+    if (!own_maps && d_maps) cudaFreeAsync(d_maps, st);
     return rc;
 }
 
@@ -483,7 +420,7 @@ int wst2d_forward_host(const wst2d_plan* p, const float* x_host, int64_t B, int 
             CUDA_TRY(cudaMalloc(&hp.x[i], chunk_sig * sig_in * sizeof(float)));
             CUDA_TRY(cudaMalloc(&hp.f[i], chunk_sig * sig_out * sizeof(float)));
             CUDA_TRY(cudaMalloc(&hp.u0h[i], (size_t)p->grid_max * p->N * (p->N / 2 + 1) * sizeof(cfloat)));
-            CUDA_TRY(cudaMalloc(&hp.maps[i], chunk_sig * map_elems * sizeof(float)));
+            CUDA_TRY(cudaMalloc(&hp.maps[i], (size_t)p->grid_max * map_elems * sizeof(float)));
             if (p->ops->workspace_cfloats)
                 CUDA_TRY(cudaMalloc(&hp.ws[i], (size_t)p->grid_max * p->ops->workspace_cfloats * sizeof(cfloat)));
         }
@@ -585,23 +522,21 @@ int wst2d_debug_phase_cycles(const wst2d_plan* p, const float* x_dev, int64_t ns
     cfloat* d_u0h = nullptr; float* d_maps = nullptr; long long* d_cyc = nullptr; cfloat* d_ws = nullptr;
     CUDA_TRY(cudaMalloc(&d_u0h, (size_t)grid * p->N * (p->N / 2 + 1) * sizeof(cfloat)));
     if (p->ops->workspace_cfloats) CUDA_TRY(cudaMalloc(&d_ws, (size_t)grid * p->ops->workspace_cfloats * sizeof(cfloat)));
-    CUDA_TRY(cudaMalloc(&d_maps, (size_t)nsig * p->K * p->hout * p->hout * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&d_maps, (size_t)grid * p->K * p->hout * p->hout * sizeof(float)));
+    float* d_feats = nullptr;
+    CUDA_TRY(cudaMalloc(&d_feats, (size_t)nsig * 2 * p->K * sizeof(float)));
     CUDA_TRY(cudaMalloc(&d_cyc, kNumPhaseTags * sizeof(long long)));
-    cudaError_t e = p->ops->launch_prof(p->pt, x_dev, nsig, d_u0h, d_ws, d_maps, d_cyc, grid, nullptr);
+    cudaError_t e = p->ops->launch_prof(p->pt, x_dev, nsig, d_u0h, d_ws, nullptr, d_maps, d_feats, d_cyc, grid, nullptr);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e == cudaSuccess) e = cudaMemcpy(cycles_host, d_cyc, kNumPhaseTags * sizeof(long long), cudaMemcpyDeviceToHost);
-    cudaFree(d_u0h); cudaFree(d_maps); cudaFree(d_cyc); cudaFree(d_ws);
+    cudaFree(d_u0h); cudaFree(d_maps); cudaFree(d_cyc); cudaFree(d_ws); cudaFree(d_feats);
     if (e != cudaSuccess) return fail(WST2D_ERR_CUDA, std::string("phase profile: ") + cudaGetErrorString(e));
     return WST2D_OK;
 }
 
 int wst2d_launch_count(const wst2d_plan* p, int64_t B, int C) {
     if (!p) return fail(WST2D_ERR_ARG, "plan is NULL");
-    long long nsig = (long long)B * C;
-    if (nsig <= 0) return 0;
-    long long chunk = chunk_signals(p, nsig);
-    long long nch = (nsig + chunk - 1) / chunk;
-    return (int)(2 * nch);   // cascade + pool per chunk
+    return (long long)B * C > 0 ? 1 : 0;   // one fused cascade + pooling kernel per forward call
 }
 
 }  // extern "C"

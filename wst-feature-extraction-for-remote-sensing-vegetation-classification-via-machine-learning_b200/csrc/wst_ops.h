@@ -16,8 +16,9 @@ struct CfgOps {
     const void* kernel;
     bool (*build)(int, const float*, const float*, std::vector<float>&, TableOffsets&, std::string&);
     void (*bind)(PlanTables&, const float*, const TableOffsets&);
-    cudaError_t (*launch)(const PlanTables&, const float*, long long, cfloat*, cfloat*, float*, int, cudaStream_t);
-    cudaError_t (*launch_prof)(const PlanTables&, const float*, long long, cfloat*, cfloat*, float*, long long*, int, cudaStream_t);
+    // (tables, x, nsig, u0h scratch, workspace, maps_out | NULL, per-CTA maps scratch | NULL, feats | NULL, grid, stream)
+    cudaError_t (*launch)(const PlanTables&, const float*, long long, cfloat*, cfloat*, float*, float*, float*, int, cudaStream_t);
+    cudaError_t (*launch_prof)(const PlanTables&, const float*, long long, cfloat*, cfloat*, float*, float*, float*, long long*, int, cudaStream_t);
 };
 
 }  // namespace wst
