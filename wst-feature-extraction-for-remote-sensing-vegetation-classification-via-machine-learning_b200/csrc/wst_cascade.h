@@ -190,6 +190,15 @@ struct PlanTables {
 };
 constexpr float kSupportEps = 1e-7f;
 
+// One H x W input signal: float32 (plane of a CHW patch) or uint8 (channel of an HWC patch, stride C;
+// value / 255 in IEEE float32 like load_rgb_image, train_and_save_model.py:54).
+struct SignalSrc {
+    const float* f32;
+    const unsigned char* u8;
+    int stride;
+    WST_D float at(int idx) const { return u8 ? (float)u8[(size_t)idx * stride] / 255.0f : f32[idx]; }
+};
+
 // ------------------------------------------------------------------ executors
 // Phase tags (kind * 8 + level of the array side being processed) — only used by the cycle-profiling
 // executor of the debug entry point; the production executor ignores them.
@@ -684,7 +693,7 @@ struct Cascade {
     }
 
     // reflect-pad the H x W input into paired rows z0, S0, and U0^ -> global scratch
-    WST_D void input_stage(const float* x) {
+    WST_D void input_stage(const SignalSrc& x) {
         constexpr int P = N + 1, HALF = N / 2, PH = N / 2 + 1;
         const int H = pt.H, W = pt.W, pt_top = pt.pad_top, pt_left = pt.pad_left;
         ex.template phase<PK_INPUT * 8>([&](int tid) {
@@ -693,7 +702,7 @@ struct Cascade {
                 int sc = c - pt_left; sc = sc < 0 ? -sc : (sc >= W ? 2 * (W - 1) - sc : sc);
                 int r0 = r - pt_top; r0 = r0 < 0 ? -r0 : (r0 >= H ? 2 * (H - 1) - r0 : r0);
                 int r1 = r + HALF - pt_top; r1 = r1 < 0 ? -r1 : (r1 >= H ? 2 * (H - 1) - r1 : r1);
-                sm[r * P + c] = cmake(x[r0 * W + sc], x[r1 * W + sc]);
+                sm[r * P + c] = cmake(x.at(r0 * W + sc), x.at(r1 * W + sc));
             }
         });
         lowpass_maps<N, HOUT, HP, NT, 0>(ex, sm, 0, 1, g(0), g(0), maps, [](int) { return 0; });
@@ -793,7 +802,7 @@ struct Cascade {
         });
     }
 
-    WST_D void run(const float* x, float* feats) {
+    WST_D void run(const SignalSrc& x, float* feats) {
         input_stage(x);
         static_for<0, J>([&](auto Jc) { this->template level<decltype(Jc)::value>(); });
         if (feats) pool(feats);

@@ -5,7 +5,7 @@
 //                         SM; each CTA runs the whole scattering cascade of one (patch, channel) signal at a
 //                         time out of shared memory and pools its maps (mean / population std,
 //                         train_and_save_model.py:371-372) before moving on (wst_cascade.h)
-//   u8_to_chw_kernel      uint8 HWC -> float32 CHW / 255 (load_rgb_image, train...:51-56)
+//                         (uint8 HWC input is converted in its input stage: load_rgb_image, train...:51-56)
 //   gabor_spatial_kernel, dft_axis{0,1}_kernel, combine_filters_kernel
 //                         fp64 filter-bank construction, once per plan (wst_filters.h)
 //
@@ -37,19 +37,6 @@ int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
         if (_e != cudaSuccess)                                                                  \
             return fail(WST2D_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));    \
     } while (0)
-
-// uint8 [B][H][W][C] -> float32 [B][C][H][W] / 255
-__global__ void u8_to_chw_kernel(const uint8_t* __restrict__ in, float* __restrict__ out,
-                                 long long B, int C, int HW) {
-    const long long total = B * C * (long long)HW;
-    for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total;
-         o += (long long)gridDim.x * blockDim.x) {
-        long long b = o / ((long long)C * HW);
-        int r = (int)(o - b * (long long)C * HW);
-        int c = r / HW, p = r - c * HW;
-        out[o] = (float)in[(b * HW + p) * C + c] / 255.0f;
-    }
-}
 
 // ------------------------------------------------------------------------------------------------
 // filter bank (fp64, once per plan)
@@ -239,7 +226,7 @@ __global__ void fma_peak_kernel(float* out, int iters) {
 // want the maps they live in a per-CTA scratch (grid x K*h*w floats, L2-resident) instead of HBM.
 // own_*: caller-provided scratch (host path) sized for grid_max CTAs; when NULL the scratch is stream-ordered
 // (cudaMallocAsync from the device's default pool).
-int forward_impl(const wst2d_plan* p, const float* x_dev, long long nsig, float* feats_dev,
+int forward_impl(const wst2d_plan* p, const void* x_dev, int x_u8_channels, long long nsig, float* feats_dev,
                  float* maps_dev, cudaStream_t st, cfloat* own_u0h = nullptr, float* own_maps = nullptr,
                  cfloat* own_ws = nullptr) {
     if (nsig == 0) return WST2D_OK;
@@ -257,7 +244,7 @@ int forward_impl(const wst2d_plan* p, const float* x_dev, long long nsig, float*
         rc = fail(WST2D_ERR_CUDA, std::string("cudaMallocAsync(scratch): ") + cudaGetErrorString(e));
     } else {
         prof_mark(p, p->prof_cascade, st);
-        e = p->ops->launch(p->pt, x_dev, nsig, d_u0h, d_ws, maps_dev, maps_dev ? nullptr : d_maps, feats_dev, grid, st);
+        e = p->ops->launch(p->pt, x_dev, x_u8_channels, nsig, d_u0h, d_ws, maps_dev, maps_dev ? nullptr : d_maps, feats_dev, grid, st);
         prof_mark(p, p->prof_cascade, st);
         if (e != cudaSuccess) rc = fail(WST2D_ERR_CUDA, std::string("cascade launch: ") + cudaGetErrorString(e));
     }
@@ -369,7 +356,7 @@ int wst2d_forward(const wst2d_plan* p, const float* x_dev, int64_t B, int C, flo
     if (!x_dev) return fail(WST2D_ERR_ARG, "x_dev is NULL");
     if (!feats_dev && !maps_dev) return fail(WST2D_ERR_ARG, "both outputs are NULL");
     DeviceGuard guard(p->device);
-    return forward_impl(p, x_dev, (long long)B * C, feats_dev, maps_dev, (cudaStream_t)cuda_stream);
+    return forward_impl(p, x_dev, 0, (long long)B * C, feats_dev, maps_dev, (cudaStream_t)cuda_stream);
 }
 
 int wst2d_forward_u8(const wst2d_plan* p, const uint8_t* x_dev, int64_t B, int C, float* feats_dev,
@@ -380,16 +367,8 @@ int wst2d_forward_u8(const wst2d_plan* p, const uint8_t* x_dev, int64_t B, int C
     if (!x_dev) return fail(WST2D_ERR_ARG, "x_dev is NULL");
     if (!feats_dev && !maps_dev) return fail(WST2D_ERR_ARG, "both outputs are NULL");
     DeviceGuard guard(p->device);
-    cudaStream_t st = (cudaStream_t)cuda_stream;
-    const size_t n = (size_t)B * C * p->H * p->W;
-    float* d_x = nullptr;
-    CUDA_TRY(cudaMallocAsync(&d_x, n * sizeof(float), st));
-    long long blocks = (long long)((n + 255) / 256);
-    if (blocks > 148 * 32) blocks = 148 * 32;
-    u8_to_chw_kernel<<<(unsigned)blocks, 256, 0, st>>>(x_dev, d_x, B, C, p->H * p->W);
-    int rc = forward_impl(p, d_x, (long long)B * C, feats_dev, maps_dev, st);
-    cudaFreeAsync(d_x, st);
-    return rc;
+    // the cascade's input stage reads the uint8 HWC pixels itself (value / 255, channel stride C)
+    return forward_impl(p, x_dev, C, (long long)B * C, feats_dev, maps_dev, (cudaStream_t)cuda_stream);
 }
 
 int wst2d_forward_host(const wst2d_plan* p, const float* x_host, int64_t B, int C, float* feats_host) {
@@ -434,7 +413,7 @@ int wst2d_forward_host(const wst2d_plan* p, const float* x_host, int64_t B, int 
         cudaError_t e = cudaMemcpyAsync(hp.x[i], x_host + (size_t)s0 * sig_in, n * sig_in * sizeof(float),
                                         cudaMemcpyHostToDevice, hp.st[i]);
         if (e != cudaSuccess) { rc = fail(WST2D_ERR_CUDA, std::string("H2D: ") + cudaGetErrorString(e)); break; }
-        rc = forward_impl(p, hp.x[i], n, hp.f[i], nullptr, hp.st[i], hp.u0h[i], hp.maps[i], hp.ws[i]);
+        rc = forward_impl(p, hp.x[i], 0, n, hp.f[i], nullptr, hp.st[i], hp.u0h[i], hp.maps[i], hp.ws[i]);
         if (rc != WST2D_OK) break;
         e = cudaMemcpyAsync(feats_host + (size_t)s0 * sig_out, hp.f[i], n * sig_out * sizeof(float),
                             cudaMemcpyDeviceToHost, hp.st[i]);
@@ -526,7 +505,7 @@ int wst2d_debug_phase_cycles(const wst2d_plan* p, const float* x_dev, int64_t ns
     float* d_feats = nullptr;
     CUDA_TRY(cudaMalloc(&d_feats, (size_t)nsig * 2 * p->K * sizeof(float)));
     CUDA_TRY(cudaMalloc(&d_cyc, kNumPhaseTags * sizeof(long long)));
-    cudaError_t e = p->ops->launch_prof(p->pt, x_dev, nsig, d_u0h, d_ws, nullptr, d_maps, d_feats, d_cyc, grid, nullptr);
+    cudaError_t e = p->ops->launch_prof(p->pt, x_dev, 0, nsig, d_u0h, d_ws, nullptr, d_maps, d_feats, d_cyc, grid, nullptr);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e == cudaSuccess) e = cudaMemcpy(cycles_host, d_cyc, kNumPhaseTags * sizeof(long long), cudaMemcpyDeviceToHost);
     cudaFree(d_u0h); cudaFree(d_maps); cudaFree(d_cyc); cudaFree(d_ws); cudaFree(d_feats);
