@@ -67,7 +67,7 @@ int emu_fft2(int M, int dir, float* data) {
         const cfloat* in = reinterpret_cast<const cfloat*>(data);
         cfloat* out = reinterpret_cast<cfloat*>(data);
         if (dir < 0) {
-            for (int r = 0; r < m; ++r) for (int c = 0; c < m; ++c) sm[r * P + c] = in[r * m + c];
+            for (int r = 0; r < m; ++r) for (int c = 0; c < m; ++c) sm[Fft1<m>::pos_s(r) * P + Fft1<m>::pos_s(c)] = in[r * m + c];
             fft_lines_fwd<m, m, P, 1, 256, 0, 0>(ex, sm.data(), 1, 0, tw.data());   // rows
             fft_lines_fwd<m, m, 1, P, 256, 0, 0>(ex, sm.data(), 1, 0, tw.data());   // columns
             for (int k = 0; k < m; ++k) for (int l = 0; l < m; ++l) out[k * m + l] = sm[Fft1<m>::pi(k) * P + Fft1<m>::pi(l)];
@@ -75,7 +75,7 @@ int emu_fft2(int M, int dir, float* data) {
             for (int k = 0; k < m; ++k) for (int l = 0; l < m; ++l) sm[Fft1<m>::pi(k) * P + Fft1<m>::pi(l)] = in[k * m + l];
             fft_lines_inv<m, m, 1, P, 256, 0, 0>(ex, sm.data(), 1, 0, tw.data());
             fft_lines_inv<m, m, P, 1, 256, 0, 0>(ex, sm.data(), 1, 0, tw.data());
-            for (int r = 0; r < m; ++r) for (int c = 0; c < m; ++c) out[r * m + c] = sm[r * P + c];
+            for (int r = 0; r < m; ++r) for (int c = 0; c < m; ++c) out[r * m + c] = sm[Fft1<m>::pos_s(r) * P + Fft1<m>::pos_s(c)];
         }
     };
     switch (M) {

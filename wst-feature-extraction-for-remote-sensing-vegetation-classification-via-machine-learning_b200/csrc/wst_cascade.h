@@ -47,9 +47,17 @@ constexpr int kSmemCfloats = 27000;      // data region budget (216,000 B) of th
 constexpr int kGlobalCfloats = 1 << 24;  // data region budget of the global-workspace variant (128 MiB per CTA, never reached)
 
 // ------------------------------------------------------------------ 1-D factorisation n = R1*R2
+// Prime-factor (Good-Thomas) split n = P * Q with P the power-of-two part and Q the odd part: the two passes
+// need no twiddles at all.  Used whenever both radices fit in registers (2 <= P <= 16, 3 <= Q <= 24).
+WST_CX int fft_pfa_Q(int n) {
+    if (n <= 18) return 0;
+    int odd = n; while (odd % 2 == 0) odd /= 2;
+    int p2 = n / odd;
+    return (odd >= 3 && odd <= 24 && p2 >= 2 && p2 <= 16) ? odd : 0;
+}
 WST_CX int fft_R2(int n) {               // contiguous radix
     if (n <= 18) return n;                 // one in-register pass
-    if (n == 20) return 5;                 // 4 x 5: more, smaller butterflies keep 512 threads busy on 20 x 20 arrays
+    if (fft_pfa_Q(n) > 0) return fft_pfa_Q(n);
     int odd = n; while (odd % 2 == 0) odd /= 2;
     int best = 0; long best_score = 1L << 60;
     for (int r2 = odd; r2 <= 24 && r2 <= n; r2 *= 2) {
@@ -72,12 +80,33 @@ WST_CX int fft_R2(int n) {               // contiguous radix
 WST_CX int fft_R1(int n) { return fft_R2(n) > 0 ? n / fft_R2(n) : 0; }
 WST_CX bool fft_supported(int n) { return n >= 2 && n % 2 == 0 && fft_R2(n) > 0; }
 
+// In-place two-pass transform of length N = R1 * R2 (strided radix R1, contiguous radix R2).
+//   Cooley-Tukey (PFA == false): frequency k is stored at (k % R1)*R2 + k / R1, space is in natural order, and
+//     one twiddle multiply sits between the passes.
+//   Good-Thomas (PFA == true, R1 and R2 coprime): frequency k is stored at (k*u % R1)*R2 + (k*v % R2) with
+//     u = R2^-1 mod R1, v = R1^-1 mod R2; sample i of the spatial side at (i % R1)*R2 + (i % R2); no twiddles.
+//     Because R1 is even and R2 odd, samples i and i + N/2 sit exactly N/2 storage slots apart, which is what
+//     the row-pairing of the real-input transforms relies on.
 template <int N> struct Fft1 {
     static constexpr int R2 = fft_R2(N);
     static constexpr int R1 = N / R2;
     static_assert(R2 > 0 && R1 * R2 == N, "unsupported FFT length");
+    static constexpr bool PFA = (R1 > 1) && fft_pfa_Q(N) == R2;
+    static constexpr int U = PFA ? cx_modinv(R2, R1) : 0;
+    static constexpr int V = PFA ? cx_modinv(R1, R2) : 0;
     // storage position of frequency k
-    static WST_HD int pi(int k) { if constexpr (R1 == 1) return k; else return (k % R1) * R2 + k / R1; }
+    static WST_HD int pi(int k) {
+        if constexpr (R1 == 1) return k;
+        else if constexpr (PFA) return ((k * U) % R1) * R2 + (k * V) % R2;
+        else return (k % R1) * R2 + k / R1;
+    }
+    // storage position of spatial sample i, and its inverse
+    static WST_HD int pos_s(int i) {
+        if constexpr (PFA) return (i % R1) * R2 + (i % R2); else return i;
+    }
+    static WST_HD int inv_pos_s(int p) {
+        if constexpr (PFA) return ((p / R2) * R2 * U + (p % R2) * R1 * V) % N; else return p;
+    }
 };
 
 // ------------------------------------------------------------------ geometry shared by host and device
@@ -246,7 +275,7 @@ WST_D void pass_strided(int tid, cfloat* base, int narr, int AS, const cfloat* t
         static_for<0, R1>([&](auto K) {
             constexpr int k = decltype(K)::value;
             cfloat v = a[k];
-            if constexpr (TW && k > 0) {
+            if constexpr (TW && !Fft1<M>::PFA && k > 0) {
                 cfloat w = tw[k * R2 + i2];
                 v = (DIR < 0) ? cmul(v, w) : cmulc(v, w);
             }
@@ -270,7 +299,7 @@ WST_D void pass_contig(int tid, cfloat* base, int narr, int AS, const cfloat* tw
         static_for<0, R2>([&](auto I) {
             constexpr int i = decltype(I)::value;
             cfloat o = v[i];
-            if constexpr (TW && R1 > 1 && i > 0) {
+            if constexpr (TW && !Fft1<M>::PFA && R1 > 1 && i > 0) {
                 cfloat w = tw[k1 * R2 + i];
                 o = (DIR < 0) ? cmul(o, w) : cmulc(o, w);
             }
@@ -698,11 +727,13 @@ struct Cascade {
         const int H = pt.H, W = pt.W, pt_top = pt.pad_top, pt_left = pt.pad_left;
         ex.template phase<PK_INPUT * 8>([&](int tid) {
             for (int o = tid; o < HALF * N; o += NT) {
-                int c = o % N, r = o / N;
+                const int cs = o % N, rs = o / N;                      // storage column / row (row < N/2)
+                const int c = Fft1<N>::inv_pos_s(cs), r = Fft1<N>::inv_pos_s(rs);   // padded-image coordinates
+                const int rp = r + HALF < N ? r + HALF : r + HALF - N;              // the row stored N/2 slots below
                 int sc = c - pt_left; sc = sc < 0 ? -sc : (sc >= W ? 2 * (W - 1) - sc : sc);
                 int r0 = r - pt_top; r0 = r0 < 0 ? -r0 : (r0 >= H ? 2 * (H - 1) - r0 : r0);
-                int r1 = r + HALF - pt_top; r1 = r1 < 0 ? -r1 : (r1 >= H ? 2 * (H - 1) - r1 : r1);
-                sm[r * P + c] = cmake(x.at(r0 * W + sc), x.at(r1 * W + sc));
+                int r1 = rp - pt_top; r1 = r1 < 0 ? -r1 : (r1 >= H ? 2 * (H - 1) - r1 : r1);
+                sm[rs * P + cs] = cmake(x.at(r0 * W + sc), x.at(r1 * W + sc));
             }
         });
         lowpass_maps<N, HOUT, HP, NT, 0>(ex, sm, 0, 1, g(0), g(0), maps, [](int) { return 0; });

@@ -86,8 +86,10 @@ inline bool build_tables(int L, const float* psi_hat, const float* phi_hat,
             }
         if (worst > 2e-6 * phi00) { err = "low-pass filter is not separable (max dev " + std::to_string(worst) + ")"; return false; }
     }
-    for (int j = 0; j < J; ++j) {
-        int m = N >> j, s = m / NS;
+    static_for<0, J>([&](auto Jc) {
+        constexpr int j = decltype(Jc)::value;
+        constexpr int m = C::msize(j);
+        const int s = m / NS;
         for (int dim = 0; dim < 2; ++dim) {
             std::vector<double> a(m), g(m);
             for (int k = 0; k < m; ++k) {
@@ -101,13 +103,13 @@ inline bool build_tables(int L, const float* psi_hat, const float* phi_hat,
                 g[x] = acc / (double)m;
             }
             float* G = buf.data() + (dim == 0 ? off.gr[j] : off.gc[j]);
-            for (int x = 0; x < m; ++x)
+            for (int x = 0; x < m; ++x)                            // rows of G follow the spatial storage order
                 for (int i = 0; i < HOUT; ++i) {
                     int idx = (((i + 1) * s - x) % m + m) % m;
-                    G[(size_t)x * HP + i] = (float)g[idx];
+                    G[(size_t)Fft1<m>::pos_s(x) * HP + i] = (float)g[idx];
                 }
         }
-    }
+    });
 
     // ---- wavelets, periodised per level (planar), with their supports
     // smallest cyclic interval of [0, n) covering all flagged positions, packed lo << 16 | len
