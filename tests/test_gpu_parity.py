@@ -17,7 +17,8 @@ pytestmark = pytest.mark.gpu
 
 TOL = 1e-4
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-CONFIGS = [(32, 2, 8), (64, 3, 8), (128, 4, 8), (128, 2, 8), (32, 3, 6)]
+CONFIGS = [(32, 2, 8), (64, 3, 8), (128, 4, 8), (128, 2, 8), (32, 3, 6),
+           (32, 1, 8), (64, 2, 8), (128, 3, 8), (32, 4, 8), (64, 4, 8)]
 
 
 def floored_rel(a, b):

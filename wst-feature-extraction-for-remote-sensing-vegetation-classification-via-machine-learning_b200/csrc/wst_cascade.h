@@ -191,7 +191,8 @@ struct Cfg {
         for (int j = 0; j < J; ++j) if (lp_fused(msize(j), has_children(j)) || (j > 0 && lp_fused(msize(j), false))) return true;
         return false;
     }
-    static constexpr int LP_SLOTS = 40;         // (array, row-chunk) partial maps held between the two reduce phases
+    // (array, row-chunk) partial maps held between the two reduce phases: ~10 KB, at least one slot per array
+    static constexpr int LP_SLOTS = cx_max(8, cx_min(40, 2560 / (HOUT * HOUT)));
     static WST_CX int lpbuf_floats() { return any_fused() ? LP_SLOTS * HOUT * HOUT : 0; }
     // bytes of dynamic shared memory, and of per-CTA global workspace (0 for the shared-memory variant)
     static WST_CX size_t smem_bytes() {
