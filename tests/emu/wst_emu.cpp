@@ -13,6 +13,10 @@
 #include "wst_tables.h"
 #include "wst_filters.h"
 
+#ifndef WST_EMU_CONFIG_FILE
+#define WST_EMU_CONFIG_FILE "wst_configs.inc"     // tests may substitute a shorter list to compile faster
+#endif
+
 using namespace wst;
 
 namespace {
@@ -93,7 +97,7 @@ int emu_forward(int N, int J, int L, int max_order, int H, int W, const float* p
                 const float* phi_hat, const float* x, int nsig, float* maps_out, float* feats_out) {
 #define CFG(n, j) if (N == n && J == j) return run_cfg<Cfg<n, j>>(L, max_order, H, W, psi_hat, phi_hat, x, nsig, maps_out, feats_out, g_err);
 #define CFGG(n, j) if (N == n && J == j) return run_cfg<Cfg<n, j, 256, true>>(L, max_order, H, W, psi_hat, phi_hat, x, nsig, maps_out, feats_out, g_err);
-#include "wst_configs.inc"
+#include WST_EMU_CONFIG_FILE
 #undef CFG
 #undef CFGG
     g_err = "emu_forward: unsupported (N, J)";
@@ -144,7 +148,7 @@ int emu_query(int N, int J, int* smem_bytes, int* gp, int* hout) {
 #define CFG(n, j) if (N == n && J == j) CFGQ(Cfg<n COMMA j>)
 #define CFGG(n, j) if (N == n && J == j) CFGQ(Cfg<n COMMA j COMMA 256 COMMA true>)
 #define COMMA ,
-#include "wst_configs.inc"
+#include WST_EMU_CONFIG_FILE
 #undef CFG
 #undef CFGG
     return -2;

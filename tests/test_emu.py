@@ -46,3 +46,40 @@ def test_cascade_vs_oracle(M, J, L, mo):
     assert floored_rel(feats[:, 0], ref.mean(axis=(-2, -1))) <= 1e-4 / 4       # in-kernel pooling
     tau = 1e-3 * np.abs(ref.mean(axis=(-2, -1))).max(axis=1, keepdims=True)
     assert float((np.abs(feats[:, 1] - ref.std(axis=(-2, -1))) / np.maximum(ref.std(axis=(-2, -1)), tau)).max()) <= 1e-4 / 4
+
+
+def test_kernels_stay_in_bounds_under_asan(tmp_path):
+    """compute-sanitizer is not available on the GPU pool, so the bounds check is done here: the emulation is
+    rebuilt with AddressSanitizer and exact-size shared-memory buffers (data region, twiddles, low-pass tables,
+    reduction buffer are separate heap blocks) and the full cascade is replayed in a subprocess."""
+    import os
+    import subprocess
+    import sys
+    src = open(os.path.join(emu.HERE, "wst_emu.cpp")).read().replace("C::smem_cfloats() + 64", "C::smem_cfloats()")
+    cpp = tmp_path / "wst_emu_asan.cpp"
+    cpp.write_text(src)
+    (tmp_path / "small_configs.inc").write_text("CFG(40, 2)\nCFG(48, 3)\nCFG(80, 3)\nCFG(36, 1)\nCFG(64, 4)\n")
+    lib = tmp_path / "libwst_emu_asan.so"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address", "-fno-omit-frame-pointer", "-fPIC",
+                    "-shared", "-DWST_EMU_CONFIG_FILE=\"small_configs.inc\"", "-I", str(tmp_path), "-I", emu.CSRC,
+                    str(cpp), "-o", str(lib)], check=True)
+    asan = subprocess.run(["g++", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    code = (
+        "import ctypes, numpy as np, sys\n"
+        "sys.path.insert(0, %r)\n"
+        "from oracle import Scattering2D\n"
+        "lib = ctypes.CDLL(%r)\n"
+        "lib.emu_forward.argtypes = [ctypes.c_int] * 6 + [ctypes.c_void_p] * 3 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]\n"
+        "for M, J, L in [(32, 2, 8), (32, 3, 6), (64, 3, 8), (32, 1, 8), (32, 4, 8)]:\n"
+        "    S = Scattering2D(J=J, shape=(M, M), L=L, cache_filters=True)\n"
+        "    psi = np.ascontiguousarray(np.stack([p['levels'][0] for p in S.psi]), np.float32)\n"
+        "    phi = np.ascontiguousarray(S.phi['levels'][0], np.float32)\n"
+        "    N = S._M_padded; K = 1 + L * J + L * L * J * (J - 1) // 2; h = N // 2 ** J - 2\n"
+        "    x = np.random.default_rng(0).random((1, M, M), dtype=np.float32)\n"
+        "    out = np.empty((1, K, h, h), np.float32); f = np.empty((1, 2, K), np.float32)\n"
+        "    rc = lib.emu_forward(N, J, L, 2, M, M, psi.ctypes.data, phi.ctypes.data, x.ctypes.data, 1, out.ctypes.data, f.ctypes.data)\n"
+        "    assert rc == 0 and np.isfinite(out).all() and np.isfinite(f).all()\n"
+        "print('clean')\n" % (emu.ROOT, str(lib)))
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
+    assert r.returncode == 0 and "clean" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
