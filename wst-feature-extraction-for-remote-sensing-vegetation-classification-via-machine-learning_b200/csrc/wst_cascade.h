@@ -526,7 +526,64 @@ WST_D void product_fold(int tid, const cfloat* uh, const float* filt, int rows, 
     constexpr int F = MP / MC, PC = MC + 1, AS = MC * (MC + 1);
     constexpr bool SPARSE = F >= 4;
     constexpr float scale = 1.0f / ((float)F * (float)F * (float)MC * (float)MC);
-    if constexpr (!SPARSE) {
+    if constexpr (!SPARSE && GS <= 2 && MC % 2 == 0 && MP % 4 == 0) {
+        // dense, few orientations per pass (the 80 x 80 children and the full-resolution parents, where only
+        // one or two arrays fit): these phases are issue-bound and the index arithmetic is shared by only GS
+        // accumulators, so each thread takes two adjacent outputs (l even, l+1): one 8/16-byte filter load and
+        // one row/mirror computation serve both.
+        constexpr int HM = MP / 2, PH = MP / 2 + 1;
+        for (int o = tid; o < MC * (MC / 2); o += NT) {
+            const int lc = (o % (MC / 2)) * 2, kc = o / (MC / 2);
+            float ar[2][GS], ai[2][GS];
+            static_for<0, 2 * GS>([&](auto E) { ar[decltype(E)::value / GS][decltype(E)::value % GS] = 0.f;
+                                                ai[decltype(E)::value / GS][decltype(E)::value % GS] = 0.f; });
+            float w[F * F][2][GS];
+            cfloat u[F * F][2];
+            static_for<0, F>([&](auto A) {
+                constexpr int a = decltype(A)::value;
+                const int k = kc + a * MC;
+                const cfloat* rd = uh + Fft1<MP>::pi(k) * PH;                       // row k, columns 0..MP/2
+                const cfloat* rm = uh + Fft1<MP>::pi(k == 0 ? 0 : MP - k) * PH;       // row -k for the mirrored half
+                static_for<0, F>([&](auto B) {
+                    constexpr int b = decltype(B)::value, sl = a * F + b;
+                    const int l = lc + b * MC;                                      // even
+                    const float* fp = filt + ((size_t)k * MP + l) * GS;
+                    if constexpr (GS == 2) {
+                        float4 t = *reinterpret_cast<const float4*>(fp);
+                        w[sl][0][0] = t.x; w[sl][0][1] = t.y; w[sl][1][0] = t.z; w[sl][1][1] = t.w;
+                    } else {
+                        float2 t = *reinterpret_cast<const float2*>(fp);
+                        w[sl][0][0] = t.x; w[sl][1][0] = t.y;
+                    }
+                    // U(k, l) and U(k, l+1) from the Hermitian half spectrum
+                    if (l + 1 <= HM) { u[sl][0] = rd[l]; u[sl][1] = rd[l + 1]; }
+                    else if (l >= HM + 1) { cfloat p = rm[MP - l], q = rm[MP - l - 1];
+                                            u[sl][0] = cmake(p.x, -p.y); u[sl][1] = cmake(q.x, -q.y); }
+                    else { cfloat q = rm[MP - l - 1]; u[sl][0] = rd[l]; u[sl][1] = cmake(q.x, -q.y); }   // l == MP/2
+                });
+            });
+            static_for<0, F * F>([&](auto S) {
+                constexpr int sl = decltype(S)::value;
+                static_for<0, 2>([&](auto Pp) {
+                    constexpr int p = decltype(Pp)::value;
+                    static_for<0, GS>([&](auto G) {
+                        constexpr int g = decltype(G)::value;
+                        ar[p][g] += u[sl][p].x * w[sl][p][g];
+                        ai[p][g] += u[sl][p].y * w[sl][p][g];
+                    });
+                });
+            });
+            cfloat* orow = out + Fft1<MC>::pi(kc) * PC;
+            static_for<0, 2>([&](auto Pp) {
+                constexpr int p = decltype(Pp)::value;
+                cfloat* op = orow + Fft1<MC>::pi(lc + p);
+                static_for<0, GS>([&](auto G) {
+                    constexpr int g = decltype(G)::value;
+                    op[g * AS] = cmake(ar[p][g] * scale, ai[p][g] * scale);
+                });
+            });
+        }
+    } else if constexpr (!SPARSE) {
         // dense: all F*F aliases of U outputs per thread are loaded as one straight-line batch
         constexpr int U = cx_max(1, cx_min(8, 32 / (F * F * (GS + 2))));
         for (int o0 = tid; o0 < MC * MC; o0 += NT * U) {
