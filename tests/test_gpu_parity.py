@@ -239,3 +239,13 @@ def test_full_size_properties(wst, M, J):
     # checksum against the oracle on a sample
     ref = oracle64(M, J, 8)(x[idx].cpu().numpy())
     assert floored_rel(fs[:, :, 0].cpu().numpy().reshape(3, -1), ref.mean(axis=(-2, -1)).reshape(3, -1)) <= TOL
+
+
+def test_against_torch_fft_dataflow(wst):
+    """Independent fp32 cross-check: kymatio's dataflow executed with torch.fft (cuFFT) on the same GPU."""
+    from tests.torch_fft_baseline import TorchFFTScattering2D
+    for M, J in [(32, 2), (64, 3)]:
+        x = torch.rand(4, 2, M, M, device="cuda")
+        ref = TorchFFTScattering2D(J, (M, M))(x.reshape(-1, M, M)).cpu().numpy()
+        _, maps = wst.get_plan(M, M, J, 8).forward(x, False, True)
+        assert floored_rel(maps.cpu().numpy().reshape(8, -1), ref.reshape(8, -1)) <= TOL
