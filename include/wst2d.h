@@ -63,6 +63,17 @@ int wst2d_forward(const wst2d_plan* plan, const float* x_dev, int64_t B, int C,
 int wst2d_forward_u8(const wst2d_plan* plan, const uint8_t* x_dev, int64_t B, int C,
                      float* feats_dev, float* maps_dev, void* cuda_stream);
 
+/* Whole-scene tiling (BASELINE configs[4]; the reference describes "patch extraction" from large rasters,
+ * docs/README.md:327-330, and pins rasterio/tifffile, requirements.txt:32,41, but ships no tiler): the plan's
+ * H x W window slides over raster_dev [C][Himg][Wimg] float32 with steps (stride_y, stride_x); tiles are
+ * numbered row-major over the ((Himg-H)/stride_y+1) x ((Wimg-W)/stride_x+1) grid and the tiles
+ * [tile_begin, tile_begin + tile_count) are processed straight from the raster (no tile copies), so ranks of
+ * a multi-GPU job simply take disjoint tile ranges.  feats_dev [tile_count][C][2][K], maps_dev
+ * [tile_count][C][K][h][w] or NULL. */
+int wst2d_forward_scene(const wst2d_plan* plan, const float* raster_dev, int C, int Himg, int Wimg,
+                        int stride_y, int stride_x, int64_t tile_begin, int64_t tile_count,
+                        float* feats_dev, float* maps_dev, void* cuda_stream);
+
 /* Host-buffer convenience path (what a drop-in extractor calls): x_host [B][C][H][W] float32 and
  * feats_host [B][C][2][K] live in host memory (pinned for full overlap); copies are chunked and
  * double-buffered against compute on two internal streams.  Synchronous on return. */

@@ -41,7 +41,7 @@ int run_cfg(int L, int max_order, int H, int W, const float* psi_hat, const floa
         for (auto& v : lpbuf) v = NAN;
         Cascade<C, HostExec<C::NT>> prog{ex, pt, sm.data(), twsm.data(), gsm.data(), lpbuf.data(), u0h.data(), maps_out + s * map_sz};
         prog.load_twiddles();
-        SignalSrc src{x + (size_t)s * H * W, nullptr, 1};
+        SignalSrc src{x + (size_t)s * H * W, nullptr, 1, W};
         prog.run(src, feats_out ? feats_out + (size_t)s * 2 * pt.K : nullptr);
     }
     return 0;

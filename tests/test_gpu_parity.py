@@ -249,3 +249,24 @@ def test_against_torch_fft_dataflow(wst):
         ref = TorchFFTScattering2D(J, (M, M))(x.reshape(-1, M, M)).cpu().numpy()
         _, maps = wst.get_plan(M, M, J, 8).forward(x, False, True)
         assert floored_rel(maps.cpu().numpy().reshape(8, -1), ref.reshape(8, -1)) <= TOL
+
+
+def test_scene_tiler_equals_explicit_tiles(wst):
+    """N2 / BASELINE configs[4]: tiles read straight from a [C, Himg, Wimg] raster (overlapping stride, ragged
+    edge dropped like a sliding window) give bit-identical features to cutting the tiles first; tile ranges
+    shard the grid."""
+    plan = wst.get_plan(64, 64, 3, 8)
+    raster = torch.rand(4, 200, 300, device="cuda")
+    ny, nx = plan.tile_grid(200, 300, stride=(48, 64))
+    assert (ny, nx) == (3, 4)
+    feats, maps = plan.forward_scene(raster, stride=(48, 64), want_maps=True)
+    tiles = torch.stack([raster[:, ty * 48:ty * 48 + 64, tx * 64:tx * 64 + 64] for ty in range(ny) for tx in range(nx)])
+    f_ref, m_ref = plan.forward(tiles.contiguous(), True, True)
+    assert torch.equal(feats, f_ref) and torch.equal(maps, m_ref)
+    lo, hi = wst.shard_range(ny * nx, 1, 2)
+    part, _ = plan.forward_scene(raster, stride=(48, 64), tile_range=(lo, hi))
+    assert torch.equal(part, f_ref[lo:hi])
+    flat, grid = wst.scene_features(raster, 64, 3, stride=(48, 64))
+    assert grid == (3, 4) and torch.equal(flat, wst.to_block(f_ref))
+    with pytest.raises(RuntimeError, match="tile range"):
+        plan.forward_scene(raster, stride=(48, 64), tile_range=(0, 13))

@@ -21,7 +21,7 @@ from . import _lib
 from ._parallel import shard_range, shard_sizes, gather_features
 
 __all__ = [
-    "Plan", "get_plan", "scattering_features", "scattering_maps", "features_from_host",
+    "Plan", "get_plan", "scattering_features", "scattering_maps", "features_from_host", "scene_features",
     "Scattering2D", "ScatteringNumPy2D", "ScatteringTorch2D",
     "extract_wst_features", "extract_wst_features_interleaved", "extract_wst_features_gray",
     "compute_scattering_coefficients", "extract_wst_features_batch", "num_coefficients",
@@ -108,6 +108,32 @@ class Plan:
                       feats.data_ptr() if feats is not None else None,
                       maps.data_ptr() if maps is not None else None,
                       ctypes.c_void_p(stream)))
+        return feats, maps
+
+    # -- whole-scene tiling -------------------------------------------------------------------
+    def tile_grid(self, Himg, Wimg, stride=None):
+        """(ny, nx) tiles of the plan's H x W window over a Himg x Wimg raster with the given (sy, sx) step."""
+        sy, sx = (self.H, self.W) if stride is None else ((stride, stride) if isinstance(stride, int) else stride)
+        return (Himg - self.H) // sy + 1, (Wimg - self.W) // sx + 1
+
+    def forward_scene(self, raster, stride=None, tile_range=None, want_maps=False):
+        """raster: [C, Himg, Wimg] float32 CUDA tensor.  Tiles (row-major over tile_grid) tile_range=(begin, end)
+        — default all — are processed straight from the raster: feats [ntiles, C, 2, K] (and maps)."""
+        if not (isinstance(raster, torch.Tensor) and raster.is_cuda and raster.dim() == 3
+                and raster.dtype == torch.float32 and raster.is_contiguous()):
+            raise RuntimeError("raster must be a contiguous float32 CUDA tensor [C, Himg, Wimg].")
+        C, Himg, Wimg = raster.shape
+        sy, sx = (self.H, self.W) if stride is None else ((stride, stride) if isinstance(stride, int) else stride)
+        ny, nx = self.tile_grid(Himg, Wimg, (sy, sx))
+        lo, hi = (0, ny * nx) if tile_range is None else tile_range
+        n = hi - lo
+        feats = torch.empty((n, C, 2, self.K), dtype=torch.float32, device=raster.device)
+        maps = torch.empty((n, C, self.K, self.h, self.w), dtype=torch.float32, device=raster.device) if want_maps else None
+        if n > 0:
+            stream = torch.cuda.current_stream(raster.device).cuda_stream
+            _lib.check(_lib.load().wst2d_forward_scene(self._h, raster.data_ptr(), C, Himg, Wimg, sy, sx, lo, n,
+                                                       feats.data_ptr(), maps.data_ptr() if want_maps else None,
+                                                       ctypes.c_void_p(stream)))
         return feats, maps
 
     # -- host path ---------------------------------------------------------------------------
@@ -214,6 +240,21 @@ def scattering_maps(x, J, L=8, max_order=2):
     plan = get_plan(x.shape[-2], x.shape[-1], J, L, max_order, x.device)
     _, maps = plan.forward(x, want_features=False, want_maps=True)
     return maps
+
+
+def scene_features(raster, tile, J, L=8, max_order=2, stride=None, rank=0, world_size=1, gather=False):
+    """Whole-scene tiling (BASELINE configs[4]): slide a tile x tile window over raster [C, Himg, Wimg] (CUDA,
+    float32), extract per-tile features, sharding the tiles contiguously over world_size ranks.
+    Returns (feats [ntiles_local or ntiles, C*2*K], (ny, nx)); with gather=True every rank gets all tiles in
+    row-major tile order through gather_features (NCCL over NVLink)."""
+    plan = get_plan(tile, tile, J, L, max_order, raster.device)
+    ny, nx = plan.tile_grid(raster.shape[1], raster.shape[2], stride)
+    lo, hi = shard_range(ny * nx, rank, world_size)
+    feats, _ = plan.forward_scene(raster, stride, (lo, hi))
+    flat = to_block(feats)
+    if gather and world_size > 1:
+        flat = gather_features(flat, ny * nx)
+    return flat, (ny, nx)
 
 
 def features_from_host(x, J, L=8, max_order=2, layout="block", device=None):

@@ -10,7 +10,7 @@ WST2D_OK, WST2D_ERR_ARG, WST2D_ERR_UNSUPPORTED, WST2D_ERR_CUDA = 0, -1, -2, -3
 SYMBOLS = ["wst2d_plan_create", "wst2d_plan_destroy", "wst2d_query", "wst2d_forward", "wst2d_forward_u8",
            "wst2d_forward_host", "wst2d_plan_filters", "wst2d_launch_count", "wst2d_last_error",
            "wst2d_version", "wst2d_profile", "wst2d_profile_read", "wst2d_fma_peak",
-           "wst2d_debug_phase_cycles"]
+           "wst2d_debug_phase_cycles", "wst2d_forward_scene"]
 
 _lib = None
 
@@ -31,6 +31,7 @@ def load():
     lib.wst2d_forward.argtypes = [vp, vp, i64, i32, vp, vp, vp]
     lib.wst2d_forward_u8.argtypes = [vp, vp, i64, i32, vp, vp, vp]
     lib.wst2d_forward_host.argtypes = [vp, vp, i64, i32, vp]
+    lib.wst2d_forward_scene.argtypes = [vp, vp, i32, i32, i32, i32, i32, i64, i64, vp, vp, vp]
     lib.wst2d_plan_filters.argtypes = [vp, vp, vp]
     lib.wst2d_launch_count.argtypes = [vp, i64, i32]
     lib.wst2d_profile.argtypes = [vp, i32]

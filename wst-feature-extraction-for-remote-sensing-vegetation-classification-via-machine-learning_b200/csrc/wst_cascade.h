@@ -225,9 +225,43 @@ constexpr float kSupportEps = 1e-7f;
 struct SignalSrc {
     const float* f32;
     const unsigned char* u8;
-    int stride;
-    WST_D float at(int idx) const { return u8 ? (float)u8[(size_t)idx * stride] / 255.0f : f32[idx]; }
+    int stride;          // element stride (C for interleaved uint8 pixels, 1 otherwise)
+    int pitch;           // elements per image row (W for a patch; the raster width for a tile of a scene)
+    WST_D float at(int r, int c) const {
+        const size_t idx = (size_t)r * pitch + c;
+        return u8 ? (float)u8[idx * stride] / 255.0f : f32[idx];
+    }
 };
+
+// Where the signals of one launch come from (kernel parameter).
+//   mode 0: float32 [nsig][H][W]                      (planes of CHW patches)
+//   mode 1: uint8   [nsig / C][H][W][C]               (HWC patches, load_rgb_image order)
+//   mode 2: float32 raster [C][Himg][Wimg], tiles of H x W taken every (sy, sx) pixels, nx tiles per tile row;
+//           signal s = (tile tile0 + s / C, channel s % C) — the whole-scene tiler of BASELINE configs[4]
+struct InputDesc {
+    const void* ptr;
+    int mode, C;
+    int Himg, Wimg, nx, sy, sx;
+    long long tile0;
+};
+
+WST_D SignalSrc signal_source(const InputDesc& in, long long s, int H, int W) {
+    SignalSrc src;
+    src.f32 = nullptr; src.u8 = nullptr; src.stride = 1; src.pitch = W;
+    if (in.mode == 1) {
+        const long long b = s / in.C;
+        src.u8 = static_cast<const unsigned char*>(in.ptr) + (size_t)b * H * W * in.C + (s - b * in.C);
+        src.stride = in.C;
+    } else if (in.mode == 2) {
+        const long long t = in.tile0 + s / in.C;
+        const int c = (int)(s % in.C), ty = (int)(t / in.nx), tx = (int)(t % in.nx);
+        src.f32 = static_cast<const float*>(in.ptr) + ((size_t)c * in.Himg + (size_t)ty * in.sy) * in.Wimg + (size_t)tx * in.sx;
+        src.pitch = in.Wimg;
+    } else {
+        src.f32 = static_cast<const float*>(in.ptr) + (size_t)s * H * W;
+    }
+    return src;
+}
 
 // ------------------------------------------------------------------ executors
 // Phase tags (kind * 8 + level of the array side being processed) — only used by the cycle-profiling
@@ -791,7 +825,7 @@ struct Cascade {
                 int sc = c - pt_left; sc = sc < 0 ? -sc : (sc >= W ? 2 * (W - 1) - sc : sc);
                 int r0 = r - pt_top; r0 = r0 < 0 ? -r0 : (r0 >= H ? 2 * (H - 1) - r0 : r0);
                 int r1 = rp - pt_top; r1 = r1 < 0 ? -r1 : (r1 >= H ? 2 * (H - 1) - r1 : r1);
-                sm[rs * P + cs] = cmake(x.at(r0 * W + sc), x.at(r1 * W + sc));
+                sm[rs * P + cs] = cmake(x.at(r0, sc), x.at(r1, sc));
             }
         });
         lowpass_maps<N, HOUT, HP, NT, 0>(ex, sm, 0, 1, g(0), g(0), maps, [](int) { return 0; });

@@ -16,7 +16,7 @@ namespace {
 typedef Cfg<WST_CFG_N, WST_CFG_J, WST_CFG_NT, (WST_CFG_GLOBAL != 0)> ThisCfg;
 
 template <class C, class Exec>
-__device__ __forceinline__ void run_cascade(Exec& ex, const PlanTables& pt, const void* x, int x_u8_channels,
+__device__ __forceinline__ void run_cascade(Exec& ex, const PlanTables& pt, const InputDesc& in,
                                             long long nsig, cfloat* u0h_scratch, cfloat* workspace, float* maps_out,
                                             float* maps_scratch, float* feats) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -25,7 +25,6 @@ __device__ __forceinline__ void run_cascade(Exec& ex, const PlanTables& pt, cons
     cfloat* twsm = C::WS_GLOBAL ? sbase : sbase + C::smem_cfloats();
     float* gsm = reinterpret_cast<float*>(twsm + C::tw_total);
     float* lpbuf = gsm + C::g_total;
-    const size_t sig_elems = (size_t)pt.H * pt.W;
     const size_t map_elems = (size_t)pt.K * C::HOUT * C::HOUT;
     Cascade<C, Exec> prog{ex, pt, sm, twsm, gsm, lpbuf,
                           u0h_scratch + (size_t)blockIdx.x * (C::N * (C::N / 2 + 1)), nullptr};
@@ -33,17 +32,7 @@ __device__ __forceinline__ void run_cascade(Exec& ex, const PlanTables& pt, cons
     for (long long s = blockIdx.x; s < nsig; s += gridDim.x) {
         // maps go to the caller's buffer, or to this CTA's own (L2-resident) scratch when only features are wanted
         prog.maps = maps_out ? maps_out + (size_t)s * map_elems : maps_scratch + (size_t)blockIdx.x * map_elems;
-        SignalSrc src;
-        if (x_u8_channels > 0) {      // uint8 [B][H][W][C]: signal s = (patch s / C, channel s % C)
-            const long long b = s / x_u8_channels;
-            src.f32 = nullptr;
-            src.u8 = static_cast<const unsigned char*>(x) + (size_t)b * sig_elems * x_u8_channels + (s - b * x_u8_channels);
-            src.stride = x_u8_channels;
-        } else {
-            src.f32 = static_cast<const float*>(x) + (size_t)s * sig_elems;
-            src.u8 = nullptr;
-            src.stride = 1;
-        }
+        const SignalSrc src = signal_source(in, s, pt.H, pt.W);
         prog.run(src, feats ? feats + (size_t)s * 2 * pt.K : nullptr);
     }
 }
@@ -52,41 +41,41 @@ __device__ __forceinline__ void run_cascade(Exec& ex, const PlanTables& pt, cons
 // time (wst_cascade.h).
 template <class C>
 __global__ void __launch_bounds__(C::NT, 1)
-cascade_kernel(const PlanTables pt, const void* __restrict__ x, int x_u8_channels, long long nsig, cfloat* u0h_scratch,
+cascade_kernel(const PlanTables pt, const InputDesc in, long long nsig, cfloat* u0h_scratch,
                cfloat* workspace, float* maps_out, float* maps_scratch, float* feats) {
     DevExec ex;
-    run_cascade<C>(ex, pt, x, x_u8_channels, nsig, u0h_scratch, workspace, maps_out, maps_scratch, feats);
+    run_cascade<C>(ex, pt, in, nsig, u0h_scratch, workspace, maps_out, maps_scratch, feats);
 }
 
 // Debug twin: same program, executor that accumulates clock64() per phase tag; CTA 0's totals -> cycles.
 template <class C>
 __global__ void __launch_bounds__(C::NT, 1)
-cascade_prof_kernel(const PlanTables pt, const void* __restrict__ x, int x_u8_channels, long long nsig, cfloat* u0h_scratch,
+cascade_prof_kernel(const PlanTables pt, const InputDesc in, long long nsig, cfloat* u0h_scratch,
                     cfloat* workspace, float* maps_out, float* maps_scratch, float* feats, long long* cycles) {
     __shared__ long long acc[kNumPhaseTags];
     for (int i = threadIdx.x; i < kNumPhaseTags; i += C::NT) acc[i] = 0;
     __syncthreads();
     ProfExec ex{acc};
-    run_cascade<C>(ex, pt, x, x_u8_channels, nsig, u0h_scratch, workspace, maps_out, maps_scratch, feats);
+    run_cascade<C>(ex, pt, in, nsig, u0h_scratch, workspace, maps_out, maps_scratch, feats);
     if (blockIdx.x == 0)
         for (int i = threadIdx.x; i < kNumPhaseTags; i += C::NT) cycles[i] = acc[i];
 }
 
 template <class C>
-cudaError_t launch_cascade(const PlanTables& pt, const void* x, int x_u8_channels, long long nsig, cfloat* u0h, cfloat* ws,
+cudaError_t launch_cascade(const PlanTables& pt, const InputDesc& in, long long nsig, cfloat* u0h, cfloat* ws,
                            float* maps_out, float* maps_scratch, float* feats, int grid, cudaStream_t st) {
-    cascade_kernel<C><<<grid, C::NT, C::smem_bytes(), st>>>(pt, x, x_u8_channels, nsig, u0h, ws, maps_out, maps_scratch, feats);
+    cascade_kernel<C><<<grid, C::NT, C::smem_bytes(), st>>>(pt, in, nsig, u0h, ws, maps_out, maps_scratch, feats);
     return cudaGetLastError();
 }
 
 template <class C>
-cudaError_t launch_cascade_prof(const PlanTables& pt, const void* x, int x_u8_channels, long long nsig, cfloat* u0h, cfloat* ws,
+cudaError_t launch_cascade_prof(const PlanTables& pt, const InputDesc& in, long long nsig, cfloat* u0h, cfloat* ws,
                                 float* maps_out, float* maps_scratch, float* feats, long long* cycles, int grid,
                                 cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(cascade_prof_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)C::smem_bytes());
     if (e != cudaSuccess) return e;
-    cascade_prof_kernel<C><<<grid, C::NT, C::smem_bytes(), st>>>(pt, x, x_u8_channels, nsig, u0h, ws, maps_out, maps_scratch, feats, cycles);
+    cascade_prof_kernel<C><<<grid, C::NT, C::smem_bytes(), st>>>(pt, in, nsig, u0h, ws, maps_out, maps_scratch, feats, cycles);
     return cudaGetLastError();
 }
 

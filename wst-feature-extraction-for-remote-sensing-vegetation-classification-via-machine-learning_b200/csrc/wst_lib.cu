@@ -226,7 +226,13 @@ __global__ void fma_peak_kernel(float* out, int iters) {
 // want the maps they live in a per-CTA scratch (grid x K*h*w floats, L2-resident) instead of HBM.
 // own_*: caller-provided scratch (host path) sized for grid_max CTAs; when NULL the scratch is stream-ordered
 // (cudaMallocAsync from the device's default pool).
-int forward_impl(const wst2d_plan* p, const void* x_dev, int x_u8_channels, long long nsig, float* feats_dev,
+InputDesc plain_input(const void* ptr, int u8_channels) {
+    InputDesc in{};
+    in.ptr = ptr; in.mode = u8_channels > 0 ? 1 : 0; in.C = u8_channels > 0 ? u8_channels : 1;
+    return in;
+}
+
+int forward_impl(const wst2d_plan* p, const InputDesc& in, long long nsig, float* feats_dev,
                  float* maps_dev, cudaStream_t st, cfloat* own_u0h = nullptr, float* own_maps = nullptr,
                  cfloat* own_ws = nullptr) {
     if (nsig == 0) return WST2D_OK;
@@ -244,7 +250,7 @@ int forward_impl(const wst2d_plan* p, const void* x_dev, int x_u8_channels, long
         rc = fail(WST2D_ERR_CUDA, std::string("cudaMallocAsync(scratch): ") + cudaGetErrorString(e));
     } else {
         prof_mark(p, p->prof_cascade, st);
-        e = p->ops->launch(p->pt, x_dev, x_u8_channels, nsig, d_u0h, d_ws, maps_dev, maps_dev ? nullptr : d_maps, feats_dev, grid, st);
+        e = p->ops->launch(p->pt, in, nsig, d_u0h, d_ws, maps_dev, maps_dev ? nullptr : d_maps, feats_dev, grid, st);
         prof_mark(p, p->prof_cascade, st);
         if (e != cudaSuccess) rc = fail(WST2D_ERR_CUDA, std::string("cascade launch: ") + cudaGetErrorString(e));
     }
@@ -356,7 +362,7 @@ int wst2d_forward(const wst2d_plan* p, const float* x_dev, int64_t B, int C, flo
     if (!x_dev) return fail(WST2D_ERR_ARG, "x_dev is NULL");
     if (!feats_dev && !maps_dev) return fail(WST2D_ERR_ARG, "both outputs are NULL");
     DeviceGuard guard(p->device);
-    return forward_impl(p, x_dev, 0, (long long)B * C, feats_dev, maps_dev, (cudaStream_t)cuda_stream);
+    return forward_impl(p, plain_input(x_dev, 0), (long long)B * C, feats_dev, maps_dev, (cudaStream_t)cuda_stream);
 }
 
 int wst2d_forward_u8(const wst2d_plan* p, const uint8_t* x_dev, int64_t B, int C, float* feats_dev,
@@ -368,7 +374,26 @@ int wst2d_forward_u8(const wst2d_plan* p, const uint8_t* x_dev, int64_t B, int C
     if (!feats_dev && !maps_dev) return fail(WST2D_ERR_ARG, "both outputs are NULL");
     DeviceGuard guard(p->device);
     // the cascade's input stage reads the uint8 HWC pixels itself (value / 255, channel stride C)
-    return forward_impl(p, x_dev, C, (long long)B * C, feats_dev, maps_dev, (cudaStream_t)cuda_stream);
+    return forward_impl(p, plain_input(x_dev, C), (long long)B * C, feats_dev, maps_dev, (cudaStream_t)cuda_stream);
+}
+
+int wst2d_forward_scene(const wst2d_plan* p, const float* raster_dev, int C, int Himg, int Wimg, int stride_y,
+                        int stride_x, int64_t tile_begin, int64_t tile_count, float* feats_dev, float* maps_dev,
+                        void* cuda_stream) {
+    if (!p) return fail(WST2D_ERR_ARG, "plan is NULL");
+    if (C < 1 || stride_y < 1 || stride_x < 1) return fail(WST2D_ERR_ARG, "C and the tile strides must be positive");
+    if (Himg < p->H || Wimg < p->W) return fail(WST2D_ERR_ARG, "raster is smaller than one tile");
+    const long long ny = (Himg - p->H) / stride_y + 1, nx = (Wimg - p->W) / stride_x + 1;
+    if (tile_begin < 0 || tile_count < 0 || tile_begin + tile_count > ny * nx)
+        return fail(WST2D_ERR_ARG, "tile range outside the " + std::to_string(ny) + " x " + std::to_string(nx) + " tile grid");
+    if (tile_count == 0) return WST2D_OK;
+    if (!raster_dev) return fail(WST2D_ERR_ARG, "raster_dev is NULL");
+    if (!feats_dev && !maps_dev) return fail(WST2D_ERR_ARG, "both outputs are NULL");
+    DeviceGuard guard(p->device);
+    InputDesc in{};
+    in.ptr = raster_dev; in.mode = 2; in.C = C; in.Himg = Himg; in.Wimg = Wimg; in.nx = (int)nx;
+    in.sy = stride_y; in.sx = stride_x; in.tile0 = tile_begin;
+    return forward_impl(p, in, (long long)tile_count * C, feats_dev, maps_dev, (cudaStream_t)cuda_stream);
 }
 
 int wst2d_forward_host(const wst2d_plan* p, const float* x_host, int64_t B, int C, float* feats_host) {
@@ -413,7 +438,7 @@ int wst2d_forward_host(const wst2d_plan* p, const float* x_host, int64_t B, int 
         cudaError_t e = cudaMemcpyAsync(hp.x[i], x_host + (size_t)s0 * sig_in, n * sig_in * sizeof(float),
                                         cudaMemcpyHostToDevice, hp.st[i]);
         if (e != cudaSuccess) { rc = fail(WST2D_ERR_CUDA, std::string("H2D: ") + cudaGetErrorString(e)); break; }
-        rc = forward_impl(p, hp.x[i], 0, n, hp.f[i], nullptr, hp.st[i], hp.u0h[i], hp.maps[i], hp.ws[i]);
+        rc = forward_impl(p, plain_input(hp.x[i], 0), n, hp.f[i], nullptr, hp.st[i], hp.u0h[i], hp.maps[i], hp.ws[i]);
         if (rc != WST2D_OK) break;
         e = cudaMemcpyAsync(feats_host + (size_t)s0 * sig_out, hp.f[i], n * sig_out * sizeof(float),
                             cudaMemcpyDeviceToHost, hp.st[i]);
@@ -505,7 +530,7 @@ int wst2d_debug_phase_cycles(const wst2d_plan* p, const float* x_dev, int64_t ns
     float* d_feats = nullptr;
     CUDA_TRY(cudaMalloc(&d_feats, (size_t)nsig * 2 * p->K * sizeof(float)));
     CUDA_TRY(cudaMalloc(&d_cyc, kNumPhaseTags * sizeof(long long)));
-    cudaError_t e = p->ops->launch_prof(p->pt, x_dev, 0, nsig, d_u0h, d_ws, nullptr, d_maps, d_feats, d_cyc, grid, nullptr);
+    cudaError_t e = p->ops->launch_prof(p->pt, plain_input(x_dev, 0), nsig, d_u0h, d_ws, nullptr, d_maps, d_feats, d_cyc, grid, nullptr);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e == cudaSuccess) e = cudaMemcpy(cycles_host, d_cyc, kNumPhaseTags * sizeof(long long), cudaMemcpyDeviceToHost);
     cudaFree(d_u0h); cudaFree(d_maps); cudaFree(d_cyc); cudaFree(d_ws); cudaFree(d_feats);

@@ -16,10 +16,9 @@ struct CfgOps {
     const void* kernel;
     bool (*build)(int, const float*, const float*, std::vector<float>&, TableOffsets&, std::string&);
     void (*bind)(PlanTables&, const float*, const TableOffsets&);
-    // x_u8_channels == 0: x is float32 [nsig][H][W]; > 0: x is uint8 [nsig / C][H][W][C] with C = x_u8_channels
-    // (tables, x, x_u8_channels, nsig, u0h scratch, workspace, maps_out | NULL, per-CTA maps scratch | NULL, feats | NULL, grid, stream)
-    cudaError_t (*launch)(const PlanTables&, const void*, int, long long, cfloat*, cfloat*, float*, float*, float*, int, cudaStream_t);
-    cudaError_t (*launch_prof)(const PlanTables&, const void*, int, long long, cfloat*, cfloat*, float*, float*, float*, long long*, int, cudaStream_t);
+    // (tables, input descriptor, nsig, u0h scratch, workspace, maps_out | NULL, per-CTA maps scratch | NULL, feats | NULL, grid, stream)
+    cudaError_t (*launch)(const PlanTables&, const InputDesc&, long long, cfloat*, cfloat*, float*, float*, float*, int, cudaStream_t);
+    cudaError_t (*launch_prof)(const PlanTables&, const InputDesc&, long long, cfloat*, cfloat*, float*, float*, float*, long long*, int, cudaStream_t);
 };
 
 }  // namespace wst
