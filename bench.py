@@ -34,12 +34,14 @@ CONFIGS = {   # name -> (M, J, L, max_order, C, default per-GPU batch)
     "cfg2": (64, 3, 8, 2, 3, 16384),
     "cfg3": (128, 4, 8, 2, 3, 4096),
     "repo": (128, 2, 8, 2, 3, 4096),
+    "cfg5": (512, 5, 8, 2, 4, 148),
 }
 WORKLOAD_NAMES = {
     "cfg1": "Scattering2D J=2 L=8 max_order=2, 32x32 RGB patches (BASELINE configs[0])",
     "cfg2": "Scattering2D J=3 L=8 max_order=2, 64x64 RGB patches (BASELINE configs[1])",
     "cfg3": "Scattering2D J=4 L=8 max_order=2, 128x128 RGB patches, batch sharded across GPUs (BASELINE configs[2])",
     "repo": "Scattering2D J=2 L=8 max_order=2, 128x128 RGB patches (the reference's own setting)",
+    "cfg5": "Scattering2D J=5 L=8 max_order=2, 512x512 4-band tiles (BASELINE configs[4]; global-workspace cascade)",
 }
 
 
@@ -99,7 +101,7 @@ def cpu_baseline(M, J, L, mo, C):
     from oracle import extract_wst_features_training
     rng = np.random.default_rng(0)
     big = M >= 128
-    nA, nB = (2, 8) if big else (4, 32)
+    nA, nB = (1, 1) if M >= 512 else ((2, 8) if big else (4, 32))
     x = (rng.integers(0, 256, (max(nA, nB), C, M, M)) / 255.0).astype(np.float32)
     t0 = time.perf_counter()
     for b in range(nA):
@@ -110,7 +112,7 @@ def cpu_baseline(M, J, L, mo, C):
     for b in range(nB):
         extract_wst_features_training(x[b], J=J, L=L, max_order=mo, cache_filters=True)
     bb = nB / (time.perf_counter() - t0)
-    per_core = 2 if big else 8
+    per_core = 1 if M >= 512 else (2 if big else 8)
     c, cores, done = cpu_all_cores(M, J, L, mo, C, per_core)
     return {
         "value": round(c, 3), "unit": "patches/s", "cores": cores, "kind": "port",
