@@ -4,7 +4,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import wst_b200
-CFG = {"cfg1": (32, 2), "cfg2": (64, 3), "cfg3": (128, 4), "repo": (128, 2)}
+CFG = {"cfg1": (32, 2), "cfg2": (64, 3), "cfg3": (128, 4), "repo": (128, 2), "cfg5": (512, 5)}
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
 waves = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 M, J = CFG[name]

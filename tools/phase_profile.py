@@ -5,11 +5,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import wst_b200
 
-CFG = {"cfg1": (32, 2), "cfg2": (64, 3), "cfg3": (128, 4), "repo": (128, 2)}
+CFG = {"cfg1": (32, 2), "cfg2": (64, 3), "cfg3": (128, 4), "repo": (128, 2), "cfg5": (512, 5)}
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
 M, J = CFG[name]
 plan = wst_b200.get_plan(M, M, J, 8)
-nsig_per_cta = 4
+nsig_per_cta = 4 if M < 512 else 1
 B = 148 * nsig_per_cta // 3 + 1
 x = torch.rand(B, 3, M, M, device="cuda")
 plan.phase_cycles(x)

@@ -296,13 +296,16 @@ template <int NT> struct HostExec {
 // are bank-conflict free for 64-bit accesses.
 
 // radix-R1 butterflies over elements {k1*R2 + i2}, optional twiddle after the butterfly.
-template <int M, int DIR, bool TW, int NL, int LS, int ES, int NT>
+// SUBFAST: consecutive threads take consecutive butterflies of the same line instead of the same butterfly of
+// consecutive lines.  Used by the global-workspace variant for row transforms, where it is what coalesces.
+template <int M, int DIR, bool TW, int NL, int LS, int ES, int NT, bool SUBFAST = false>
 WST_D void pass_strided(int tid, cfloat* base, int narr, int AS, const cfloat* tw) {
     constexpr int R1 = Fft1<M>::R1, R2 = Fft1<M>::R2;
     const int total = narr * R2 * NL;
     for (int b = tid; b < total; b += NT) {
-        int line = b % NL, r = b / NL;
-        int i2 = r % R2, g = r / R2;
+        int line, i2, g;
+        if constexpr (SUBFAST) { i2 = b % R2; int r = b / R2; line = r % NL; g = r / NL; }
+        else { line = b % NL; int r = b / NL; i2 = r % R2; g = r / R2; }
         cfloat* p = base + g * AS + line * LS + i2 * ES;
         cfloat a[R1];
         static_for<0, R1>([&](auto K) { constexpr int k = decltype(K)::value; a[k] = p[k * R2 * ES]; });
@@ -320,13 +323,14 @@ WST_D void pass_strided(int tid, cfloat* base, int narr, int AS, const cfloat* t
 }
 
 // radix-R2 butterflies over contiguous elements {k1*R2 + i2}, optional twiddle after.
-template <int M, int DIR, bool TW, int NL, int LS, int ES, int NT>
+template <int M, int DIR, bool TW, int NL, int LS, int ES, int NT, bool SUBFAST = false>
 WST_D void pass_contig(int tid, cfloat* base, int narr, int AS, const cfloat* tw) {
     constexpr int R1 = Fft1<M>::R1, R2 = Fft1<M>::R2;
     const int total = narr * R1 * NL;
     for (int b = tid; b < total; b += NT) {
-        int line = b % NL, r = b / NL;
-        int k1 = r % R1, g = r / R1;
+        int line, k1, g;
+        if constexpr (SUBFAST) { k1 = b % R1; int r = b / R1; line = r % NL; g = r / NL; }
+        else { line = b % NL; int r = b / NL; k1 = r % R1; g = r / R1; }
         cfloat* p = base + g * AS + line * LS + k1 * R2 * ES;
         cfloat v[R2];
         static_for<0, R2>([&](auto I) { constexpr int i = decltype(I)::value; v[i] = p[i * ES]; });
@@ -344,20 +348,22 @@ WST_D void pass_contig(int tid, cfloat* base, int narr, int AS, const cfloat* tw
 }
 
 // forward 1-D transforms of all lines: natural -> digit-swapped
-template <int M, int NL, int LS, int ES, int NT, int TAG_S, int TAG_C, class Exec>
+template <int M, int NL, int LS, int ES, int NT, int TAG_S, int TAG_C, bool GLOB = false, class Exec>
 WST_D void fft_lines_fwd(Exec& ex, cfloat* base, int narr, int AS, const cfloat* tw) {
+    constexpr bool SF = GLOB && ES == 1;
     if constexpr (Fft1<M>::R1 > 1) {
-        ex.template phase<TAG_S>([&](int tid) { pass_strided<M, -1, true, NL, LS, ES, NT>(tid, base, narr, AS, tw); });
+        ex.template phase<TAG_S>([&](int tid) { pass_strided<M, -1, true, NL, LS, ES, NT, SF>(tid, base, narr, AS, tw); });
     }
-    ex.template phase<TAG_C>([&](int tid) { pass_contig<M, -1, false, NL, LS, ES, NT>(tid, base, narr, AS, tw); });
+    ex.template phase<TAG_C>([&](int tid) { pass_contig<M, -1, false, NL, LS, ES, NT, SF>(tid, base, narr, AS, tw); });
 }
 
 // inverse 1-D transforms of all lines: digit-swapped -> natural (unnormalised)
-template <int M, int NL, int LS, int ES, int NT, int TAG_C, int TAG_S, class Exec>
+template <int M, int NL, int LS, int ES, int NT, int TAG_C, int TAG_S, bool GLOB = false, class Exec>
 WST_D void fft_lines_inv(Exec& ex, cfloat* base, int narr, int AS, const cfloat* tw) {
-    ex.template phase<TAG_C>([&](int tid) { pass_contig<M, +1, true, NL, LS, ES, NT>(tid, base, narr, AS, tw); });
+    constexpr bool SF = GLOB && ES == 1;
+    ex.template phase<TAG_C>([&](int tid) { pass_contig<M, +1, true, NL, LS, ES, NT, SF>(tid, base, narr, AS, tw); });
     if constexpr (Fft1<M>::R1 > 1) {
-        ex.template phase<TAG_S>([&](int tid) { pass_strided<M, +1, false, NL, LS, ES, NT>(tid, base, narr, AS, tw); });
+        ex.template phase<TAG_S>([&](int tid) { pass_strided<M, +1, false, NL, LS, ES, NT, SF>(tid, base, narr, AS, tw); });
     }
 }
 
@@ -369,7 +375,7 @@ WST_D void fft_lines_inv(Exec& ex, cfloat* base, int narr, int AS, const cfloat*
 //              no z :  row r, column slot (q*R2 + i2) <- (acc_r[2q], acc_r[2q+1]),  q < HOUT/2
 //              z    :  row x+M/2, slot (q*R2 + i2) <- acc_x[..],  slot ((HOUT/2+q)*R2 + i2) <- acc_{x+M/2}[..]
 //            (single-pass lengths hold whole rows: the slot is column q and the sum over y is complete).
-template <int M, int NT, bool WRITE_Z, bool LPF, int HOUT, int HP>
+template <int M, int NT, bool WRITE_Z, bool LPF, int HOUT, int HP, bool SUBFAST = false>
 WST_D void pass_rows_final(int tid, cfloat* base, int narr, int AS, const float* gc) {
     constexpr int R1 = Fft1<M>::R1, R2 = Fft1<M>::R2, P = M + 1, HALF = M / 2;
     constexpr int NV = (R1 > 1) ? R1 : R2;            // values per row held by one thread
@@ -377,8 +383,9 @@ WST_D void pass_rows_final(int tid, cfloat* base, int narr, int AS, const float*
     const int nsub = (R1 > 1) ? R2 : 1;
     const int total = narr * nsub * HALF;
     for (int b = tid; b < total; b += NT) {
-        int x = b % HALF, r = b / HALF;
-        int i2 = r % nsub, g = r / nsub;
+        int x, i2, g;
+        if constexpr (SUBFAST) { i2 = b % nsub; int r = b / nsub; x = r % HALF; g = r / HALF; }
+        else { x = b % HALF; int r = b / HALF; i2 = r % nsub; g = r / nsub; }
         cfloat* p0 = base + g * AS + x * P + i2;
         cfloat* p1 = p0 + HALF * P;
         cfloat a[NV], c[NV];
@@ -475,11 +482,11 @@ WST_D void lowpass_reduce(Exec& ex, cfloat* base, int narr, int AS, const float*
 
 // Real 2-D forward FFT of narr paired-row arrays z (stride ZS, pitch M+1, M/2 rows) into
 // half spectra U^[pi(k)][l], l = 0..M/2 (stride UHS = M*(M/2+1), pitch M/2+1).
-template <int M, int NT, int LV, class Exec>
+template <int M, int NT, int LV, bool GLOB = false, class Exec>
 WST_D void rfft2_from_pairs(Exec& ex, cfloat* z, int ZS, cfloat* uh, int narr, const cfloat* tw) {
     constexpr int P = M + 1, HALF = M / 2, PH = M / 2 + 1, UHS = M * PH;
     // rows of z (along y): natural -> swapped
-    fft_lines_fwd<M, HALF, P, 1, NT, PK_RFFT_ROW_S * 8 + LV, PK_RFFT_ROW_C * 8 + LV>(ex, z, narr, ZS, tw);
+    fft_lines_fwd<M, HALF, P, 1, NT, PK_RFFT_ROW_S * 8 + LV, PK_RFFT_ROW_C * 8 + LV, GLOB>(ex, z, narr, ZS, tw);
     // split the packed rows:  A = FFT(row x), B = FFT(row x + M/2)
     ex.template phase<PK_RFFT_SPLIT * 8 + LV>([&](int tid) {
         const int total = narr * PH * HALF;
@@ -758,7 +765,7 @@ WST_D void lowpass_maps(Exec& ex, cfloat* z, int ZS, int narr, const float* gr, 
 
 // Inverse 2-D FFT of narr digit-swapped M x M spectra (pitch M+1) + modulus (+ row-paired z for a following
 // rfft2_from_pairs) + low-pass map of every array.
-template <int M, int NT, int LV, bool WRITE_Z, int HOUT, int HP, int LPSLOTS, class Exec, class CoefFn>
+template <int M, int NT, int LV, bool WRITE_Z, int HOUT, int HP, int LPSLOTS, bool GLOB = false, class Exec, class CoefFn>
 WST_D void ifft2_modulus_lowpass(Exec& ex, cfloat* base, int narr, const cfloat* tw, const float* g,
                                  float* lpbuf, float* maps, CoefFn coef) {
     constexpr int P = M + 1, AS = M * (M + 1);
@@ -766,13 +773,13 @@ WST_D void ifft2_modulus_lowpass(Exec& ex, cfloat* base, int narr, const cfloat*
                                               : (WRITE_Z ? (HOUT <= Fft1<M>::R1) : (HOUT / 2 <= Fft1<M>::R1));
     fft_lines_inv<M, M, 1, P, NT, PK_IFFT_COL_C * 8 + LV, PK_IFFT_COL_S * 8 + LV>(ex, base, narr, AS, tw);   // columns
     if constexpr (Fft1<M>::R1 > 1) {
-        ex.template phase<PK_IFFT_ROW_C * 8 + LV>([&](int tid) { pass_contig<M, +1, true, M, P, 1, NT>(tid, base, narr, AS, tw); });
+        ex.template phase<PK_IFFT_ROW_C * 8 + LV>([&](int tid) { pass_contig<M, +1, true, M, P, 1, NT, GLOB>(tid, base, narr, AS, tw); });
     }
     if constexpr (FUSED) {
-        ex.template phase<PK_IFFT_FINAL * 8 + LV>([&](int tid) { pass_rows_final<M, NT, WRITE_Z, true, HOUT, HP>(tid, base, narr, AS, g); });
+        ex.template phase<PK_IFFT_FINAL * 8 + LV>([&](int tid) { pass_rows_final<M, NT, WRITE_Z, true, HOUT, HP, GLOB>(tid, base, narr, AS, g); });
         lowpass_reduce<M, NT, WRITE_Z, HOUT, HP, LPSLOTS, LV>(ex, base, narr, AS, g, lpbuf, maps, coef);
     } else {
-        ex.template phase<PK_IFFT_FINAL * 8 + LV>([&](int tid) { pass_rows_final<M, NT, true, false, HOUT, HP>(tid, base, narr, AS, g); });
+        ex.template phase<PK_IFFT_FINAL * 8 + LV>([&](int tid) { pass_rows_final<M, NT, true, false, HOUT, HP, GLOB>(tid, base, narr, AS, g); });
         lowpass_maps<M, HOUT, HP, NT, LV>(ex, base, AS, narr, g, g, maps, coef);
     }
 }
@@ -830,7 +837,7 @@ struct Cascade {
         });
         lowpass_maps<N, HOUT, HP, NT, 0>(ex, sm, 0, 1, g(0), g(0), maps, [](int) { return 0; });
         cfloat* uh = sm + C::OFFB(0);
-        rfft2_from_pairs<N, NT, 0>(ex, sm, 0, uh, 1, tw(0));
+        rfft2_from_pairs<N, NT, 0, C::WS_GLOBAL>(ex, sm, 0, uh, 1, tw(0));
         ex.template phase<PK_U0_STORE * 8>([&](int tid) {
             for (int o = tid; o < N * PH; o += NT) u0h[o] = uh[o];
         });
@@ -847,7 +854,7 @@ struct Cascade {
                 product_fold<MP, MC, G, NT>(tid, uh_parent, pt.psi2[J2][J1] + (size_t)grp * MP * MP * G,
                                             pt.bb2[pair_index(J2, J1)][grp][0], pt.bb2[pair_index(J2, J1)][grp][1], sm);
             });
-            ifft2_modulus_lowpass<MC, NT, J2, false, HOUT, HP, C::LP_SLOTS>(
+            ifft2_modulus_lowpass<MC, NT, J2, false, HOUT, HP, C::LP_SLOTS, C::WS_GLOBAL>(
                 ex, sm, G, tw(J2), g(J2), lpbuf, maps,
                 [&](int a) { int t2 = grp * G + a; return t2 < L ? cbase + t2 : -1; });
         }
@@ -863,13 +870,13 @@ struct Cascade {
                 product_fold<N, M, GPn, NT>(tid, u0h, pt.psi1[J1] + (size_t)grp * N * N * GPn,
                                             pt.bb1[J1][grp][0], pt.bb1[J1][grp][1], sm);
             });
-            ifft2_modulus_lowpass<M, NT, J1, C::has_children(J1), HOUT, HP, C::LP_SLOTS>(
+            ifft2_modulus_lowpass<M, NT, J1, C::has_children(J1), HOUT, HP, C::LP_SLOTS, C::WS_GLOBAL>(
                 ex, sm, GPn, tw(J1), g(J1), lpbuf, maps,
                 [&](int a) { int t1 = grp * GPn + a; return t1 < L ? 1 + J1 * L + t1 : -1; });
             if constexpr (C::has_children(J1)) {
                 if (pt.max_order >= 2) {
                     cfloat* uh = sm + C::OFFB(J1);
-                    rfft2_from_pairs<M, NT, J1>(ex, sm, C::vsz(M), uh, GPn, tw(J1));
+                    rfft2_from_pairs<M, NT, J1, C::WS_GLOBAL>(ex, sm, C::vsz(M), uh, GPn, tw(J1));
                     for (int g = 0; g < GPn; ++g) {
                         int t1 = grp * GPn + g;
                         if (t1 >= L) break;
