@@ -74,6 +74,17 @@ int wst2d_forward_scene(const wst2d_plan* plan, const float* raster_dev, int C, 
                         int stride_y, int stride_x, int64_t tile_begin, int64_t tile_count,
                         float* feats_dev, float* maps_dev, void* cuda_stream);
 
+/* The reference's "advanced statistics" extractor (extract_advanced_features,
+ * src/training/train_and_save_model.py:58-112 = src/inference/inference.py:181-235), 18 statistics per channel
+ * in the reference's order: mean std var min max range skew kurt cv p10 p25 p50 p75 p90 iqr mad grad_mean
+ * edge_density.  x_dev: float32 [B][C][H][W], or uint8 [B][H][W][C] when is_u8 != 0; out_dev: float32
+ * [B][C][18].  Needs no plan.  H*W (rounded up to a power of two for the sort) must fit in shared memory
+ * (128x128 does); inputs are assumed finite (the reference drops non-finite pixels).  Errors are reported by
+ * wst2d_advanced_stats_last_error(). */
+int wst2d_advanced_stats(int device, const void* x_dev, int is_u8, int64_t B, int C, int H, int W,
+                         float* out_dev, void* cuda_stream);
+const char* wst2d_advanced_stats_last_error(void);
+
 /* Host-buffer convenience path (what a drop-in extractor calls): x_host [B][C][H][W] float32 and
  * feats_host [B][C][2][K] live in host memory (pinned for full overlap); copies are chunked and
  * double-buffered against compute on two internal streams.  Synchronous on return. */

@@ -25,7 +25,8 @@ __all__ = [
     "Scattering2D", "ScatteringNumPy2D", "ScatteringTorch2D",
     "extract_wst_features", "extract_wst_features_interleaved", "extract_wst_features_gray",
     "compute_scattering_coefficients", "extract_wst_features_batch", "num_coefficients",
-    "compute_padding", "to_interleaved", "to_block", "shard_range", "shard_sizes", "gather_features", "fma_peak_tflops",
+    "compute_padding", "to_interleaved", "to_block", "advanced_stats", "extract_advanced_features",
+    "extract_hybrid_features", "hybrid_features", "ADVANCED_STAT_NAMES", "shard_range", "shard_sizes", "gather_features", "fma_peak_tflops",
 ]
 
 
@@ -366,6 +367,49 @@ def Scattering2D(J, shape, L=8, max_order=2, pre_pad=False, backend=None, out_ty
     if frontend == "torch":
         return ScatteringTorch2D(J, shape, L, max_order, pre_pad, backend, out_type)
     raise RuntimeError("The frontend '%s' is not valid. Must be one of 'numpy' or 'torch'." % frontend)
+
+
+# ----------------------------------------------------------------------------- advanced statistics (N3)
+ADVANCED_STAT_NAMES = ["mean", "std", "var", "min", "max", "range", "skew", "kurt", "cv", "p10", "p25", "p50", "p75",
+                       "p90", "iqr", "mad", "grad_mean", "edge_density"]        # train_and_save_model.py:402-405
+
+
+def advanced_stats(x):
+    """x: [B, C, H, W] float32 or [B, H, W, C] uint8 CUDA tensor -> [B, C, 18] float32 on the same device
+    (extract_advanced_features, train_and_save_model.py:58-112, per patch and channel)."""
+    if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 4 and x.is_contiguous()):
+        raise RuntimeError("advanced_stats expects a contiguous 4-D CUDA tensor.")
+    u8 = x.dtype == torch.uint8
+    if not u8 and x.dtype != torch.float32:
+        raise TypeError("advanced_stats expects float32 [B, C, H, W] or uint8 [B, H, W, C].")
+    B, C, H, W = (x.shape[0], x.shape[3], x.shape[1], x.shape[2]) if u8 else tuple(x.shape)
+    out = torch.empty((B, C, 18), dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    rc = lib.wst2d_advanced_stats(x.device.index or 0, x.data_ptr(), 1 if u8 else 0, B, C, H, W, out.data_ptr(),
+                                  ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+    if rc != 0:
+        msg = lib.wst2d_advanced_stats_last_error().decode()
+        raise (NotImplementedError if rc == _lib.WST2D_ERR_UNSUPPORTED else RuntimeError)("wst_b200: " + msg)
+    return out
+
+
+def extract_advanced_features(rgb_image):
+    """Drop-in for train_and_save_model.py:58-112 / inference.py:181-235: [C, H, W] float32 -> float64 [C*18]."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("wst_b200: no CUDA device available (this package has no CPU fallback).")
+    x = torch.from_numpy(np.ascontiguousarray(np.asarray(rgb_image)[None], dtype=np.float32)).cuda()
+    return advanced_stats(x)[0].reshape(-1).cpu().numpy().astype(np.float64)
+
+
+def extract_hybrid_features(rgb_image, J=2, L=8):
+    """Drop-in for train_and_save_model.py:380-387: concat([advanced stats (C*18), WST (C*2*K)]) -> float64."""
+    return np.concatenate([extract_advanced_features(rgb_image), extract_wst_features(rgb_image, J=J, L=L)])
+
+
+def hybrid_features(x, J, L=8, max_order=2):
+    """Batched device form: x [B, C, H, W] float32 CUDA -> [B, C*18 + C*2*K] (advanced stats block, then WST block)."""
+    adv = advanced_stats(x).reshape(x.shape[0], -1)
+    return torch.cat([adv, scattering_features(x, J, L, max_order)], dim=1)
 
 
 # ----------------------------------------------------------------------------- reference extractors (B1, B2)

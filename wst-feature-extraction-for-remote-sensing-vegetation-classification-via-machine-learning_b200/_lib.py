@@ -10,7 +10,8 @@ WST2D_OK, WST2D_ERR_ARG, WST2D_ERR_UNSUPPORTED, WST2D_ERR_CUDA = 0, -1, -2, -3
 SYMBOLS = ["wst2d_plan_create", "wst2d_plan_destroy", "wst2d_query", "wst2d_forward", "wst2d_forward_u8",
            "wst2d_forward_host", "wst2d_plan_filters", "wst2d_launch_count", "wst2d_last_error",
            "wst2d_version", "wst2d_profile", "wst2d_profile_read", "wst2d_fma_peak",
-           "wst2d_debug_phase_cycles", "wst2d_forward_scene"]
+           "wst2d_debug_phase_cycles", "wst2d_forward_scene", "wst2d_advanced_stats",
+           "wst2d_advanced_stats_last_error"]
 
 _lib = None
 
@@ -38,10 +39,12 @@ def load():
     lib.wst2d_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i32)]
     lib.wst2d_debug_phase_cycles.argtypes = [vp, vp, i64, vp, i32]
     lib.wst2d_fma_peak.argtypes = [i32, ctypes.POINTER(ctypes.c_double)]
+    lib.wst2d_advanced_stats.argtypes = [i32, vp, i32, i64, i32, i32, i32, vp, vp]
+    lib.wst2d_advanced_stats_last_error.restype = ctypes.c_char_p
     lib.wst2d_last_error.restype = ctypes.c_char_p
     lib.wst2d_version.restype = ctypes.c_char_p
     for name in SYMBOLS:
-        if name not in ("wst2d_last_error", "wst2d_version"):
+        if name not in ("wst2d_last_error", "wst2d_version", "wst2d_advanced_stats_last_error"):
             getattr(lib, name).restype = i32
     _lib = lib
     return lib
