@@ -85,6 +85,31 @@ int wst2d_advanced_stats(int device, const void* x_dev, int is_u8, int64_t B, in
                          float* out_dev, void* cuda_stream);
 const char* wst2d_advanced_stats_last_error(void);
 
+/* The five noise models of the reference's robustness sweep (src/preprocessing/add_noise.py:14-72:
+ * add_gaussian_noise, add_salt_and_pepper_noise, add_speckle_noise, add_poisson_noise, add_uniform_noise) for a
+ * batch of uint8 images [B][H][W][C] resident on the device; out_dev has the same shape (out_dev == img_dev is
+ * allowed) and feeds wst2d_forward_u8 directly.  intensity is the reference's 0..100 percentage.
+ *   wst2d_add_noise        draws from a counter-based generator (Philox4x32-10, key = seed, counter = element
+ *                          index): same distributions as the reference's numpy calls, different stream.
+ *   wst2d_add_noise_draws  the caller supplies the draws numpy produced for the reference, and the output is then
+ *                          the reference's bit for bit.  draws_dev: float64 [B][H][W][C] for gaussian (already
+ *                          scaled by sigma), speckle (standard normal) and uniform; int64 [B][H][W][C] Poisson
+ *                          counts; for salt_and_pepper int64 [B][2 (salt, pepper)][2 (row, col)][n_coords]
+ *                          (n_coords is ignored by the other models).
+ * Errors: wst2d_noise_last_error(). */
+enum {
+    WST2D_NOISE_GAUSSIAN = 0,
+    WST2D_NOISE_SALT_AND_PEPPER = 1,
+    WST2D_NOISE_SPECKLE = 2,
+    WST2D_NOISE_POISSON = 3,
+    WST2D_NOISE_UNIFORM = 4
+};
+int wst2d_add_noise(int device, int kind, double intensity, const uint8_t* img_dev, int64_t B, int H, int W, int C,
+                    uint64_t seed, uint8_t* out_dev, void* cuda_stream);
+int wst2d_add_noise_draws(int device, int kind, double intensity, const uint8_t* img_dev, int64_t B, int H, int W,
+                          int C, const void* draws_dev, int64_t n_coords, uint8_t* out_dev, void* cuda_stream);
+const char* wst2d_noise_last_error(void);
+
 /* Host-buffer convenience path (what a drop-in extractor calls): x_host [B][C][H][W] float32 and
  * feats_host [B][C][2][K] live in host memory (pinned for full overlap); copies are chunked and
  * double-buffered against compute on two internal streams.  Synchronous on return. */

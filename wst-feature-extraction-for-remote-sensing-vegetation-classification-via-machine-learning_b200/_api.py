@@ -26,7 +26,9 @@ __all__ = [
     "extract_wst_features", "extract_wst_features_interleaved", "extract_wst_features_gray",
     "compute_scattering_coefficients", "extract_wst_features_batch", "num_coefficients",
     "compute_padding", "to_interleaved", "to_block", "advanced_stats", "extract_advanced_features",
-    "extract_hybrid_features", "hybrid_features", "ADVANCED_STAT_NAMES", "shard_range", "shard_sizes", "gather_features", "fma_peak_tflops",
+    "extract_hybrid_features", "hybrid_features", "ADVANCED_STAT_NAMES",
+    "NOISE_TYPES", "add_noise", "add_gaussian_noise", "add_salt_and_pepper_noise", "add_speckle_noise",
+    "add_poisson_noise", "add_uniform_noise", "shard_range", "shard_sizes", "gather_features", "fma_peak_tflops",
 ]
 
 
@@ -410,6 +412,89 @@ def hybrid_features(x, J, L=8, max_order=2):
     """Batched device form: x [B, C, H, W] float32 CUDA -> [B, C*18 + C*2*K] (advanced stats block, then WST block)."""
     adv = advanced_stats(x).reshape(x.shape[0], -1)
     return torch.cat([adv, scattering_features(x, J, L, max_order)], dim=1)
+
+
+# ----------------------------------------------------------------------------- noise models (N4)
+NOISE_TYPES = ["gaussian", "salt_and_pepper", "speckle", "poisson", "uniform"]       # add_noise.py:123 / wst2d.h enum
+
+
+def add_noise(images, noise_type, intensity, seed=42, draws=None):
+    """Batched device form of add_noise.py:14-72.  images: contiguous uint8 CUDA tensor [B, H, W, C] (or [H, W, C]);
+    returns a new uint8 tensor of the same shape, ready for the uint8 ingest of the WST plan.
+
+    draws=None: the random draws come from the library's counter-based generator (seed defaults to the
+    reference's --seed 42; the stream differs from numpy's).  draws given: the reference's own numpy draws for the
+    batch — a float64 tensor shaped like `images` (gaussian: already scaled by sigma; speckle; uniform), an int64
+    tensor of Poisson counts, or for salt_and_pepper an int64 tensor [B, 2 (salt, pepper), 2 (row, col), n] — and
+    the result is then bit-identical to the reference's."""
+    if noise_type not in NOISE_TYPES:
+        raise ValueError("Unknown noise type: %s" % noise_type)                      # add_noise.py:92
+    if not (isinstance(images, torch.Tensor) and images.is_cuda and images.dtype == torch.uint8
+            and images.dim() in (3, 4) and images.is_contiguous()):
+        raise RuntimeError("add_noise expects a contiguous uint8 CUDA tensor [B, H, W, C] or [H, W, C].")
+    x = images if images.dim() == 4 else images[None]
+    B, H, W, C = x.shape
+    out = torch.empty_like(x)
+    lib = _lib.load()
+    kind = NOISE_TYPES.index(noise_type)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+    dev = x.device.index or 0
+    if draws is None:
+        rc = lib.wst2d_add_noise(dev, kind, float(intensity), x.data_ptr(), B, H, W, C, int(seed) & (2 ** 64 - 1),
+                                 out.data_ptr(), stream)
+    else:
+        want = torch.int64 if noise_type in ("poisson", "salt_and_pepper") else torch.float64
+        if not (isinstance(draws, torch.Tensor) and draws.is_cuda and draws.dtype == want and draws.is_contiguous()):
+            raise RuntimeError("add_noise: draws must be a contiguous %s CUDA tensor." % want)
+        if noise_type == "salt_and_pepper":
+            if draws.dim() != 4 or tuple(draws.shape[:3]) != (B, 2, 2):
+                raise RuntimeError("add_noise: salt_and_pepper draws must be [B, 2, 2, n].")
+            n = draws.shape[3]
+        else:
+            if draws.numel() != x.numel():
+                raise RuntimeError("add_noise: draws must have one value per image element.")
+            n = 0
+        rc = lib.wst2d_add_noise_draws(dev, kind, float(intensity), x.data_ptr(), B, H, W, C, draws.data_ptr(), n,
+                                       out.data_ptr(), stream)
+    if rc != 0:
+        msg = lib.wst2d_noise_last_error().decode()
+        raise (ValueError if rc == _lib.WST2D_ERR_ARG else RuntimeError)("wst_b200: " + msg)
+    return out if images.dim() == 4 else out[0]
+
+
+def _add_noise_image(image_array, noise_type, intensity):
+    if not torch.cuda.is_available():
+        raise RuntimeError("wst_b200: no CUDA device available (this package has no CPU fallback).")
+    a = np.ascontiguousarray(image_array)
+    if a.dtype != np.uint8 or a.ndim != 3:
+        raise ValueError("expected a uint8 image array [H, W, C]")
+    seed = int(np.random.randint(0, 2 ** 31 - 1))       # one draw from the caller's seeded numpy stream (add_noise.py:147-149)
+    return add_noise(torch.from_numpy(a).cuda(), noise_type, intensity, seed=seed).cpu().numpy()
+
+
+def add_gaussian_noise(image_array, intensity):
+    """Drop-in for add_noise.py:14-21 (uint8 [H, W, C] numpy in and out; seeded through numpy's global RNG)."""
+    return _add_noise_image(image_array, "gaussian", intensity)
+
+
+def add_salt_and_pepper_noise(image_array, intensity):
+    """Drop-in for add_noise.py:23-43, including its coordinate-range and count conventions."""
+    return _add_noise_image(image_array, "salt_and_pepper", intensity)
+
+
+def add_speckle_noise(image_array, intensity):
+    """Drop-in for add_noise.py:45-54."""
+    return _add_noise_image(image_array, "speckle", intensity)
+
+
+def add_poisson_noise(image_array, intensity):
+    """Drop-in for add_noise.py:56-65."""
+    return _add_noise_image(image_array, "poisson", intensity)
+
+
+def add_uniform_noise(image_array, intensity):
+    """Drop-in for add_noise.py:67-72."""
+    return _add_noise_image(image_array, "uniform", intensity)
 
 
 # ----------------------------------------------------------------------------- reference extractors (B1, B2)

@@ -62,9 +62,10 @@ def build_library(force=False, verbose=False):
     o = os.path.join(OBJ, "wst_lib.o")
     objs.append(o)
     jobs.append(([nvcc] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, "wst_lib.cu"), "-o", o], verbose))
-    o = os.path.join(OBJ, "wst_advstats.o")
-    objs.append(o)
-    jobs.append(([nvcc] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, "wst_advstats.cu"), "-o", o], verbose))
+    for unit in ("wst_advstats", "wst_noise"):
+        o = os.path.join(OBJ, unit + ".o")
+        objs.append(o)
+        jobs.append(([nvcc] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, unit + ".cu"), "-o", o], verbose))
     for n, j, glob in configs():
         o = os.path.join(OBJ, "wst_cfg_%d_%d.o" % (n, j))
         objs.append(o)

@@ -11,7 +11,7 @@ SYMBOLS = ["wst2d_plan_create", "wst2d_plan_destroy", "wst2d_query", "wst2d_forw
            "wst2d_forward_host", "wst2d_plan_filters", "wst2d_launch_count", "wst2d_last_error",
            "wst2d_version", "wst2d_profile", "wst2d_profile_read", "wst2d_fma_peak",
            "wst2d_debug_phase_cycles", "wst2d_forward_scene", "wst2d_advanced_stats",
-           "wst2d_advanced_stats_last_error"]
+           "wst2d_advanced_stats_last_error", "wst2d_add_noise", "wst2d_add_noise_draws", "wst2d_noise_last_error"]
 
 _lib = None
 
@@ -41,10 +41,14 @@ def load():
     lib.wst2d_fma_peak.argtypes = [i32, ctypes.POINTER(ctypes.c_double)]
     lib.wst2d_advanced_stats.argtypes = [i32, vp, i32, i64, i32, i32, i32, vp, vp]
     lib.wst2d_advanced_stats_last_error.restype = ctypes.c_char_p
+    f64, u64 = ctypes.c_double, ctypes.c_uint64
+    lib.wst2d_add_noise.argtypes = [i32, i32, f64, vp, i64, i32, i32, i32, u64, vp, vp]
+    lib.wst2d_add_noise_draws.argtypes = [i32, i32, f64, vp, i64, i32, i32, i32, vp, i64, vp, vp]
+    lib.wst2d_noise_last_error.restype = ctypes.c_char_p
     lib.wst2d_last_error.restype = ctypes.c_char_p
     lib.wst2d_version.restype = ctypes.c_char_p
     for name in SYMBOLS:
-        if name not in ("wst2d_last_error", "wst2d_version", "wst2d_advanced_stats_last_error"):
+        if name not in ("wst2d_last_error", "wst2d_version", "wst2d_advanced_stats_last_error", "wst2d_noise_last_error"):
             getattr(lib, name).restype = i32
     _lib = lib
     return lib

@@ -101,13 +101,29 @@ template <int N> struct Fft1 {
         else return (k % R1) * R2 + k / R1;
     }
     // storage position of spatial sample i, and its inverse
-    static WST_HD int pos_s(int i) {
+    static WST_CX int pos_s(int i) {
         if constexpr (PFA) return (i % R1) * R2 + (i % R2); else return i;
     }
     static WST_HD int inv_pos_s(int p) {
         if constexpr (PFA) return ((p / R2) * R2 * U + (p % R2) * R1 * V) % N; else return p;
     }
 };
+
+// ------------------------------------------------------------------ banded low-pass
+// The low-pass kernel at a level whose output stride is S = 2^(J-j) samples is a Gaussian of sigma 0.4*S samples
+// (phi has sigma 0.8 * 2^(J-1) pixels): beyond R = ceil(5.68 * 0.4 * S) samples it is below
+// 1e-7 of its peak (the same threshold the wavelet supports use).  When that band is narrow against the row length
+// (large output maps: 128x128 at J=2 keeps 32x32 outputs) the separable low-pass is evaluated as a strided
+// (2R+1)-tap convolution instead of a dense [m x HOUT] operator.
+constexpr int kLpTaps = 40;              // taps w[0..R] kept per level in the kernel parameter block
+WST_CX int lp_radius(int stride) { return stride == 2 ? 5 : stride == 4 ? 10 : stride == 8 ? 19 : stride == 16 ? 37 : 0; }
+// Level 0 holds phi as sampled in space (an exact periodised Gaussian).  Deeper levels use the corner crop of phi^,
+// whose kink at the level's Nyquist frequency gives the spatial kernel 1/d^2 tails: 4e-2 of the peak spectrum at
+// stride 2, 3e-6 at stride 4, negligible from stride 8 on.  Hence: level 0, or stride >= 8.
+WST_CX bool lp_banded(int m, int hout, int level) {
+    int s = m / (hout + 2), r = lp_radius(s);
+    return r > 0 && s * (hout + 2) == m && (2 * r + 1) * 3 <= m && (level == 0 || s >= 8);
+}
 
 // ------------------------------------------------------------------ geometry shared by host and device
 // WS_GLOBAL = false: the data region lives in shared memory (the fast path, N <= 160).
@@ -217,6 +233,10 @@ struct PlanTables {
     // block (constant bank), so the product loops have no dependent global loads.
     int bb1[kMaxJ][kMaxL][2];              // order-1: scale j at level 0
     int bb2[kMaxPairs][kMaxL][2];          // order-2: pair_index(j2, j1): scale j2 at level j1
+    // Banded low-pass taps of level j (zero where the level uses the dense operator): lpw[j][d] = weight of the
+    // sample d positions away from the output's centre, d <= lp_radius.  Read with compile-time indices, i.e. as
+    // constant-bank operands of the FMAs.
+    float lpw[kMaxJ][kLpTaps];
 };
 constexpr float kSupportEps = 1e-7f;
 
@@ -709,65 +729,160 @@ WST_D void product_fold(int tid, const cfloat* uh, const float* filt, int rows, 
 // written to maps + coef(g)*HOUT*HOUT for arrays with coef(g) >= 0.
 // Scratch: the dead second half of each array (rows >= M/2).
 template <int M, int HOUT, int HP, int NT, int LV, class Exec, class CoefFn>
-WST_D void lowpass_maps(Exec& ex, cfloat* z, int ZS, int narr, const float* gr, const float* gc,
-                        float* maps, CoefFn coef) {
-    constexpr int P = M + 1, HALF = M / 2;
-    // chunks of the x range per (array, y) so that about NT threads are busy; scratch must fit
-    constexpr int NCH_FIT = (M + 1) / HOUT < 1 ? 1 : (M + 1) / HOUT;
-    const int want = (NT + narr * M - 1) / (narr * M);
-    const int nch = want < 1 ? 1 : (want > NCH_FIT ? NCH_FIT : (want > HALF ? HALF : want));
-    const int xper = (HALF + nch - 1) / nch;
+WST_D void lowpass_maps_dense(Exec& ex, cfloat* z, int ZS, int narr, const float* gr, const float* gc,
+                              float* maps, CoefFn coef) {
+    constexpr int P = M + 1, HALF = M / 2, PT = HOUT | 1;
+    constexpr int GO1 = HOUT >= 8 ? 8 : HP, NG1 = (HOUT + GO1 - 1) / GO1;      // phase 1: outputs per thread (float4s of G)
+    constexpr int NG2 = HP / 4;                                                // phase 2: one float4 of outputs per thread
+    static_assert(PT * M <= 2 * HALF * P && GO1 % 4 == 0, "low-pass scratch must fit in the dead half of the array");
+    static_assert(HOUT < 8 || HOUT % 8 == 0, "output side must be below 8 or a multiple of 8");
+    // phase LP1: T[y][i] = sum_x Gr[x][i] * U[x][y]; thread = (array, group of GO1 outputs i, column slot y), the
+    // G rows are warp-uniform (broadcast) vector loads, the U column is read as (row x, row x + M/2) pairs.
     ex.template phase<PK_LP1 * 8 + LV>([&](int tid) {
-        const int total = narr * nch * M;
+        const int total = narr * NG1 * M;
         for (int b = tid; b < total; b += NT) {
-            int y = b % M, r = b / M;
-            int c = r % nch, g = r / nch;
+            const int y = b % M, r = b / M;
+            const int q = r % NG1, g = r / NG1;
             const cfloat* zp = z + g * ZS + y;
-            float acc[HOUT];
-            static_for<0, HOUT>([&](auto I) { acc[decltype(I)::value] = 0.f; });
-            int x0 = c * xper, x1 = x0 + xper < HALF ? x0 + xper : HALF;
-            for (int x = x0; x < x1; ++x) {
-                cfloat v = zp[x * P];
-                const float* g0 = gr + x * HP;
-                const float* g1 = gr + (x + HALF) * HP;
-                static_for<0, HP / 4>([&](auto Q) {
-                    constexpr int q = decltype(Q)::value;
-                    float4 a = *reinterpret_cast<const float4*>(g0 + 4 * q);
-                    float4 d = *reinterpret_cast<const float4*>(g1 + 4 * q);
-                    if constexpr (4 * q + 0 < HOUT) acc[4 * q + 0] += a.x * v.x + d.x * v.y;
-                    if constexpr (4 * q + 1 < HOUT) acc[4 * q + 1] += a.y * v.x + d.y * v.y;
-                    if constexpr (4 * q + 2 < HOUT) acc[4 * q + 2] += a.z * v.x + d.z * v.y;
-                    if constexpr (4 * q + 3 < HOUT) acc[4 * q + 3] += a.w * v.x + d.w * v.y;
+            const float* g0 = gr + q * GO1;
+            float acc[GO1];
+            static_for<0, GO1>([&](auto I) { acc[decltype(I)::value] = 0.f; });
+#pragma unroll 2
+            for (int x = 0; x < HALF; ++x) {
+                const cfloat v = zp[x * P];
+                static_for<0, GO1 / 4>([&](auto Q) {
+                    constexpr int k = decltype(Q)::value;
+                    const float4 a = *reinterpret_cast<const float4*>(g0 + x * HP + 4 * k);
+                    const float4 d = *reinterpret_cast<const float4*>(g0 + (x + HALF) * HP + 4 * k);
+                    acc[4 * k + 0] += a.x * v.x + d.x * v.y;
+                    acc[4 * k + 1] += a.y * v.x + d.y * v.y;
+                    acc[4 * k + 2] += a.z * v.x + d.z * v.y;
+                    acc[4 * k + 3] += a.w * v.x + d.w * v.y;
                 });
             }
-            float* tp = reinterpret_cast<float*>(z + g * ZS + HALF * P) + (c * HOUT) * M + y;
-            static_for<0, HOUT>([&](auto I) { tp[decltype(I)::value * M] = acc[decltype(I)::value]; });
+            float* tp = reinterpret_cast<float*>(z + g * ZS + HALF * P) + y * PT + q * GO1;
+            static_for<0, GO1>([&](auto I) {
+                constexpr int i = decltype(I)::value;
+                if (q * GO1 + i < HOUT) tp[i] = acc[i];
+            });
+        }
+    });
+    // phase LP2: S[i][i'] = sum_y T[y][i] * Gc[y][i']; thread = (array, float4 of outputs i', row i)
+    ex.template phase<PK_LP2 * 8 + LV>([&](int tid) {
+        const int total = narr * NG2 * HOUT;
+        for (int b = tid; b < total; b += NT) {
+            const int ir = b % HOUT, r = b / HOUT;
+            const int q = r % NG2, g = r / NG2;
+            const int cidx = coef(g);
+            if (cidx < 0) continue;
+            const float* tp = reinterpret_cast<const float*>(z + g * ZS + HALF * P) + ir;
+            const float* gq = gc + 4 * q;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+            for (int y = 0; y < M; ++y) {
+                const float t = tp[y * PT];
+                const float4 w = *reinterpret_cast<const float4*>(gq + y * HP);
+                a0 += w.x * t; a1 += w.y * t; a2 += w.z * t; a3 += w.w * t;
+            }
+            float* mp = maps + (size_t)cidx * (HOUT * HOUT) + ir * HOUT + 4 * q;
+            if (4 * q + 0 < HOUT) mp[0] = a0;
+            if (4 * q + 1 < HOUT) mp[1] = a1;
+            if (4 * q + 2 < HOUT) mp[2] = a2;
+            if (4 * q + 3 < HOUT) mp[3] = a3;
+        }
+    });
+}
+
+// Banded form of lowpass_maps for levels where lp_banded(M, HOUT): the operator is circulant, G[x][i] = w[|(i+1)*S - x|],
+// and w vanishes beyond R samples, so every output is a (2R+1)-tap strided convolution.  All positions are
+// compile-time constants (the spatial side may be stored in Good-Thomas order, Fft1<M>::pos_s), the taps are
+// constant-bank operands, and a thread produces GO consecutive outputs from one sliding window of loads.
+//   phase LP1: T[y][ir]  = sum_d w[|d|] * U[(ir+1)*S + d][y]      thread = (array, output group, y slot)
+//   phase LP2: S[ir][ic] = sum_d w[|d|] * T[(ic+1)*S + d][ir]     thread = (array, output group, ir)
+// T (pitch HOUT|1 floats) lives in the dead second half of each array, like lowpass_maps' scratch.
+template <int M, int HOUT, int NT, int LV, class Exec, class CoefFn>
+WST_D void lowpass_maps_banded(Exec& ex, cfloat* z, int ZS, int narr, const float (&w)[kLpTaps], float* maps,
+                               CoefFn coef) {
+    constexpr int P = M + 1, HALF = M / 2, S = M / (HOUT + 2), R = lp_radius(S), PT = HOUT | 1;
+    constexpr int GO = HOUT >= 8 ? 8 : HOUT, NG = (HOUT + GO - 1) / GO;        // outputs per thread, groups per line
+    static_assert(R > 0 && R < kLpTaps && PT * M <= 2 * HALF * P, "banded low-pass geometry");
+    ex.template phase<PK_LP1 * 8 + LV>([&](int tid) {
+        const int total = narr * NG * M;
+        for (int b = tid; b < total; b += NT) {
+            const int ys = b % M, r = b / M;
+            const int grp = r % NG, g = r / NG;
+            const float* zp = reinterpret_cast<const float*>(z + g * ZS + ys);
+            float* tp = reinterpret_cast<float*>(z + g * ZS + HALF * P) + ys * PT;
+            static_for<0, NG>([&](auto Gc) {
+                constexpr int G = decltype(Gc)::value;
+                if (grp != G) return;
+                constexpr int I0 = G * GO, I1 = (I0 + GO < HOUT ? I0 + GO : HOUT);      // outputs [I0, I1)
+                float acc[GO];
+                static_for<0, GO>([&](auto I) { acc[decltype(I)::value] = 0.f; });
+                static_for<(I0 + 1) * S - R, I1 * S + R + 1>([&](auto Xc) {
+                    constexpr int xx = decltype(Xc)::value;                         // window position (may wrap)
+                    constexpr int slot = Fft1<M>::pos_s(((xx % M) + M) % M);
+                    constexpr int row = slot < HALF ? slot : slot - HALF, comp = slot < HALF ? 0 : 1;
+                    const float v = zp[row * P * 2 + comp];
+                    static_for<0, GO>([&](auto I) {
+                        constexpr int i = decltype(I)::value;
+                        constexpr int d = xx - (I0 + i + 1) * S;
+                        if constexpr (I0 + i < I1 && d >= -R && d <= R) acc[i] += w[d < 0 ? -d : d] * v;
+                    });
+                });
+                static_for<0, GO>([&](auto I) {
+                    constexpr int i = decltype(I)::value;
+                    if constexpr (I0 + i < I1) tp[I0 + i] = acc[i];
+                });
+            });
         }
     });
     ex.template phase<PK_LP2 * 8 + LV>([&](int tid) {
-        const int total = narr * HOUT * HOUT;
+        const int total = narr * NG * HOUT;
         for (int b = tid; b < total; b += NT) {
-            int ic = b % HOUT, r = b / HOUT;
-            int ir = r % HOUT, g = r / HOUT;
-            int cidx = coef(g);
+            const int ir = b % HOUT, r = b / HOUT;
+            const int grp = r % NG, g = r / NG;
+            const int cidx = coef(g);
             if (cidx < 0) continue;
-            const float* tp = reinterpret_cast<const float*>(z + g * ZS + HALF * P) + ir * M;
-            float s = 0.f;
-            for (int y = 0; y < M; ++y) {
-                float t = tp[y];
-                for (int c = 1; c < nch; ++c) t += tp[c * HOUT * M + y];
-                s += t * gc[y * HP + ic];
-            }
-            maps[(size_t)cidx * (HOUT * HOUT) + ir * HOUT + ic] = s;
+            const float* tp = reinterpret_cast<const float*>(z + g * ZS + HALF * P) + ir;
+            float* mp = maps + (size_t)cidx * (HOUT * HOUT) + ir * HOUT;
+            static_for<0, NG>([&](auto Gc) {
+                constexpr int G = decltype(Gc)::value;
+                if (grp != G) return;
+                constexpr int I0 = G * GO, I1 = (I0 + GO < HOUT ? I0 + GO : HOUT);
+                float acc[GO];
+                static_for<0, GO>([&](auto I) { acc[decltype(I)::value] = 0.f; });
+                static_for<(I0 + 1) * S - R, I1 * S + R + 1>([&](auto Yc) {
+                    constexpr int yy = decltype(Yc)::value;
+                    constexpr int slot = Fft1<M>::pos_s(((yy % M) + M) % M);
+                    const float v = tp[slot * PT];
+                    static_for<0, GO>([&](auto I) {
+                        constexpr int i = decltype(I)::value;
+                        constexpr int d = yy - (I0 + i + 1) * S;
+                        if constexpr (I0 + i < I1 && d >= -R && d <= R) acc[i] += w[d < 0 ? -d : d] * v;
+                    });
+                });
+                static_for<0, GO>([&](auto I) {
+                    constexpr int i = decltype(I)::value;
+                    if constexpr (I0 + i < I1) mp[I0 + i] = acc[i];
+                });
+            });
         }
     });
+}
+
+template <int M, int HOUT, int HP, int NT, int LV, bool BAND, class Exec, class CoefFn>
+WST_D void lowpass_maps(Exec& ex, cfloat* z, int ZS, int narr, const float* gr, const float* gc,
+                        const float (&w)[kLpTaps], float* maps, CoefFn coef) {
+    if constexpr (BAND) lowpass_maps_banded<M, HOUT, NT, LV>(ex, z, ZS, narr, w, maps, coef);
+    else lowpass_maps_dense<M, HOUT, HP, NT, LV>(ex, z, ZS, narr, gr, gc, maps, coef);
 }
 
 // Inverse 2-D FFT of narr digit-swapped M x M spectra (pitch M+1) + modulus (+ row-paired z for a following
 // rfft2_from_pairs) + low-pass map of every array.
 template <int M, int NT, int LV, bool WRITE_Z, int HOUT, int HP, int LPSLOTS, bool GLOB = false, class Exec, class CoefFn>
 WST_D void ifft2_modulus_lowpass(Exec& ex, cfloat* base, int narr, const cfloat* tw, const float* g,
-                                 float* lpbuf, float* maps, CoefFn coef) {
+                                 const float (&w)[kLpTaps], float* lpbuf, float* maps, CoefFn coef) {
     constexpr int P = M + 1, AS = M * (M + 1);
     constexpr bool FUSED = (Fft1<M>::R1 == 1) ? !WRITE_Z
                                               : (WRITE_Z ? (HOUT <= Fft1<M>::R1) : (HOUT / 2 <= Fft1<M>::R1));
@@ -780,7 +895,7 @@ WST_D void ifft2_modulus_lowpass(Exec& ex, cfloat* base, int narr, const cfloat*
         lowpass_reduce<M, NT, WRITE_Z, HOUT, HP, LPSLOTS, LV>(ex, base, narr, AS, g, lpbuf, maps, coef);
     } else {
         ex.template phase<PK_IFFT_FINAL * 8 + LV>([&](int tid) { pass_rows_final<M, NT, true, false, HOUT, HP, GLOB>(tid, base, narr, AS, g); });
-        lowpass_maps<M, HOUT, HP, NT, LV>(ex, base, AS, narr, g, g, maps, coef);
+        lowpass_maps<M, HOUT, HP, NT, LV, lp_banded(M, HOUT, LV) && !GLOB>(ex, base, AS, narr, g, g, w, maps, coef);
     }
 }
 
@@ -835,7 +950,8 @@ struct Cascade {
                 sm[rs * P + cs] = cmake(x.at(r0, sc), x.at(r1, sc));
             }
         });
-        lowpass_maps<N, HOUT, HP, NT, 0>(ex, sm, 0, 1, g(0), g(0), maps, [](int) { return 0; });
+        lowpass_maps<N, HOUT, HP, NT, 0, lp_banded(N, HOUT, 0) && !C::WS_GLOBAL>(ex, sm, 0, 1, g(0), g(0), pt.lpw[0], maps,
+                                                                              [](int) { return 0; });
         cfloat* uh = sm + C::OFFB(0);
         rfft2_from_pairs<N, NT, 0, C::WS_GLOBAL>(ex, sm, 0, uh, 1, tw(0));
         ex.template phase<PK_U0_STORE * 8>([&](int tid) {
@@ -855,7 +971,7 @@ struct Cascade {
                                             pt.bb2[pair_index(J2, J1)][grp][0], pt.bb2[pair_index(J2, J1)][grp][1], sm);
             });
             ifft2_modulus_lowpass<MC, NT, J2, false, HOUT, HP, C::LP_SLOTS, C::WS_GLOBAL>(
-                ex, sm, G, tw(J2), g(J2), lpbuf, maps,
+                ex, sm, G, tw(J2), g(J2), pt.lpw[J2], lpbuf, maps,
                 [&](int a) { int t2 = grp * G + a; return t2 < L ? cbase + t2 : -1; });
         }
     }
@@ -871,7 +987,7 @@ struct Cascade {
                                             pt.bb1[J1][grp][0], pt.bb1[J1][grp][1], sm);
             });
             ifft2_modulus_lowpass<M, NT, J1, C::has_children(J1), HOUT, HP, C::LP_SLOTS, C::WS_GLOBAL>(
-                ex, sm, GPn, tw(J1), g(J1), lpbuf, maps,
+                ex, sm, GPn, tw(J1), g(J1), pt.lpw[J1], lpbuf, maps,
                 [&](int a) { int t1 = grp * GPn + a; return t1 < L ? 1 + J1 * L + t1 : -1; });
             if constexpr (C::has_children(J1)) {
                 if (pt.max_order >= 2) {

@@ -20,6 +20,7 @@ struct TableOffsets {              // offsets in floats into the flat buffer
     size_t tw[kMaxJ], gr[kMaxJ], gc[kMaxJ], psi1[kMaxJ], psi2[kMaxJ][kMaxJ];
     size_t total;
     int bb1[kMaxJ][kMaxL][2], bb2[kMaxPairs][kMaxL][2];    // support bounding boxes (copied into PlanTables)
+    float lpw[kMaxJ][kLpTaps];                             // banded low-pass taps (copied into PlanTables)
     double support_fraction;      // visited filter entries / all filter entries (diagnostic)
 };
 
@@ -86,6 +87,7 @@ inline bool build_tables(int L, const float* psi_hat, const float* phi_hat,
             }
         if (worst > 2e-6 * phi00) { err = "low-pass filter is not separable (max dev " + std::to_string(worst) + ")"; return false; }
     }
+    bool ok = true;
     static_for<0, J>([&](auto Jc) {
         constexpr int j = decltype(Jc)::value;
         constexpr int m = C::msize(j);
@@ -102,6 +104,15 @@ inline bool build_tables(int L, const float* psi_hat, const float* phi_hat,
                 for (int k = 0; k < m; ++k) acc += a[k] * std::cos(kTwoPi * (double)((k * x) % m) / (double)m);
                 g[x] = acc / (double)m;
             }
+            if constexpr (lp_banded(m, HOUT, j)) {                     // taps of the banded evaluation (same g)
+                constexpr int R = lp_radius(m / NS);
+                for (int d = 0; d <= R; ++d) off.lpw[j][d] = (float)g[d];
+                for (int d = R + 1; d < m - R; ++d)
+                    if (std::fabs(g[d]) > 1e-7 * std::fabs(g[0])) {
+                        err = "low-pass kernel of level " + std::to_string(j) + " is wider than its compiled band";
+                        ok = false;
+                    }
+            }
             float* G = buf.data() + (dim == 0 ? off.gr[j] : off.gc[j]);
             for (int x = 0; x < m; ++x)                            // rows of G follow the spatial storage order
                 for (int i = 0; i < HOUT; ++i) {
@@ -110,6 +121,8 @@ inline bool build_tables(int L, const float* psi_hat, const float* phi_hat,
                 }
         }
     });
+
+    if (!ok) return false;
 
     // ---- wavelets, periodised per level (planar), with their supports
     // smallest cyclic interval of [0, n) covering all flagged positions, packed lo << 16 | len
@@ -175,6 +188,7 @@ template <class C>
 inline void bind_tables(PlanTables& pt, const float* base, const TableOffsets& off) {
     std::memcpy(pt.bb1, off.bb1, sizeof(pt.bb1));
     std::memcpy(pt.bb2, off.bb2, sizeof(pt.bb2));
+    std::memcpy(pt.lpw, off.lpw, sizeof(pt.lpw));
     for (int j = 0; j < C::J; ++j) {
         pt.tw[j] = reinterpret_cast<const cfloat*>(base + off.tw[j]);
         pt.gr[j] = base + off.gr[j];
