@@ -83,3 +83,41 @@ def test_kernels_stay_in_bounds_under_asan(tmp_path):
     env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
     assert r.returncode == 0 and "clean" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_shipped_build_variants_vs_oracle(tmp_path):
+    """The small sides are built with fewer threads per CTA and a smaller data region than the defaults
+    (wst_b200/_build.py: SHARED_OVERRIDES, several CTAs per SM).  Group sizes and every phase's work split depend on
+    both, so the emulation is rebuilt with exactly those parameters and replayed against the oracle."""
+    import ctypes
+    import importlib
+    import subprocess
+    overrides = importlib.import_module("wst_b200._build").SHARED_OVERRIDES
+    assert overrides, "no build variants to check"
+    sizes = {(40, 2): 32, (80, 3): 64, (36, 1): 32, (72, 2): 64, (48, 3): 32, (64, 4): 32, (96, 4): 64}
+    for (N, J), (nt, budget) in sorted(overrides.items()):
+        M, L = sizes[(N, J)], 8
+        inc = tmp_path / ("cfg_%d_%d.inc" % (N, J))
+        inc.write_text("CFG(%d, %d)\n" % (N, J))
+        lib_path = tmp_path / ("libwst_emu_%d_%d.so" % (N, J))
+        subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-DWST_NT=%d" % nt,
+                        "-DWST_SMEM_BUDGET=%d" % budget, "-DWST_EMU_CONFIG_FILE=\"%s\"" % inc.name,
+                        "-I", str(tmp_path), "-I", emu.CSRC, "-I", emu.HERE, str(emu.HERE + "/wst_emu.cpp"),
+                        "-o", str(lib_path)], check=True)
+        lib = ctypes.CDLL(str(lib_path))
+        lib.emu_forward.argtypes = [ctypes.c_int] * 6 + [ctypes.c_void_p] * 3 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        rng = np.random.default_rng(N)
+        x = (rng.integers(0, 256, (2, M, M)) / 255.0).astype(np.float32)
+        S = Scattering2D(J=J, shape=(M, M), L=L, precision="double", cache_filters=True)
+        assert S._M_padded == N
+        psi = np.ascontiguousarray(np.stack([p["levels"][0] for p in S.psi]), np.float32)
+        phi = np.ascontiguousarray(S.phi["levels"][0], np.float32)
+        K, h = S(x[:1]).shape[1], N // 2 ** J - 2
+        out = np.full((2, K, h, h), np.nan, np.float32)
+        feats = np.full((2, 2, K), np.nan, np.float32)
+        rc = lib.emu_forward(N, J, L, 2, M, M, psi.ctypes.data, phi.ctypes.data, x.ctypes.data, 2, out.ctypes.data,
+                             feats.ctypes.data)
+        assert rc == 0
+        ref = S(x)
+        assert not np.isnan(out).any() and floored_rel(out, ref) <= 1e-4 / 4
+        assert floored_rel(feats[:, 0], ref.mean(axis=(-2, -1))) <= 1e-4 / 4

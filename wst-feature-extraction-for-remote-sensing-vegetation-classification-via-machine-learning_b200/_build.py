@@ -11,10 +11,26 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 OBJ = os.path.join(PKG_DIR, "_obj")
-LIB_PATH = os.path.join(PKG_DIR, "libwst_b200.so")
+LIB_PATH = os.path.join(PKG_DIR, os.environ.get("WST_BUILD_LIB", "libwst_b200.so"))
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC"]
-GLOBAL_VARIANT_THREADS = 256      # the global-workspace variant holds 2 x 24-point butterflies per thread
+# The global-workspace variant (CFGG entries: sides whose arrays do not fit in shared memory): threads per CTA (two
+# CTAs share an SM), CTAs per cluster (1: one CTA per signal; the cluster form is kept as a tuning knob, it measured
+# slower), and the data-region budget in cfloats that sizes the per-signal working set (Cfg::BUDGET).
+# The environment overrides exist for tuning runs: WST_BUILD_NTL / WST_BUILD_CL / WST_BUILD_BUDGET, and WST_BUILD_LIB
+# names the output library (the same variable selects the library at run time, see tools/tune_variants.sh).
+GLOBAL_VARIANT_THREADS = int(os.environ.get("WST_BUILD_NTL", 256))
+GLOBAL_VARIANT_CLUSTER = int(os.environ.get("WST_BUILD_CL", 1))
+GLOBAL_VARIANT_BUDGET = int(os.environ.get("WST_BUILD_BUDGET", 1 << 20))
+
+
+# Shared-memory configurations that run with other than the default 640 threads / 27000-cfloat data region:
+# {(N, J): (threads per CTA, data-region budget in cfloats)}; small sides leave room for several CTAs per SM, whose
+# barrier waits then overlap.  WST_BUILD_SHARED="N:J:threads:budget,..." overrides for tuning runs.
+SHARED_OVERRIDES = {(40, 2): (160, 6000), (80, 3): (320, 12000)}     # four / two narrower CTAs per SM (measured best)
+for _item in filter(None, os.environ.get("WST_BUILD_SHARED", "").split(",")):
+    _n, _j, _t, _b = (int(v) for v in _item.split(":"))
+    SHARED_OVERRIDES[(_n, _j)] = (_t, _b)
 
 
 def configs():
@@ -68,12 +84,21 @@ def build_library(force=False, verbose=False):
         jobs.append(([nvcc] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, unit + ".cu"), "-o", o], verbose))
     for n, j, glob in configs():
         o = os.path.join(OBJ, "wst_cfg_%d_%d.o" % (n, j))
-        objs.append(o)
         defs = ["-DWST_CFG_N=%d" % n, "-DWST_CFG_J=%d" % j]
         if glob:
-            defs += ["-DWST_CFG_GLOBAL=1", "-DWST_CFG_NT=%d" % GLOBAL_VARIANT_THREADS]
+            cl, ntl, budget = GLOBAL_VARIANT_CLUSTER, GLOBAL_VARIANT_THREADS, GLOBAL_VARIANT_BUDGET
+            o = os.path.join(OBJ, "wst_cfg_%d_%d_cl%d_t%d_b%d.o" % (n, j, cl, ntl, budget))
+            defs += ["-DWST_CFG_GLOBAL=1", "-DWST_CFG_NT=%d" % (ntl * cl), "-DWST_CFG_CL=%d" % cl,
+                     "-DWST_GLOBAL_BUDGET=%d" % budget]
+        if (n, j) in SHARED_OVERRIDES:
+            nt, budget = SHARED_OVERRIDES[(n, j)]
+            o = os.path.join(OBJ, "wst_cfg_%d_%d_t%d_b%d.o" % (n, j, nt, budget))
+            defs += ["-DWST_CFG_NT=%d" % nt, "-DWST_SMEM_BUDGET=%d" % budget]
+        objs.append(o)
         jobs.append(([nvcc] + NVCC_FLAGS + extra + defs + ["-c", os.path.join(CSRC, "wst_cfg_inst.cu"), "-o", o], verbose))
-    with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+    if not force:                       # objects carry their variant in the name: recompile only what is out of date
+        jobs = [jb for jb in jobs if _stale(jb[0][-1])]
+    with concurrent.futures.ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 4))) as ex:
         logs = list(ex.map(_compile, jobs))
     if verbose:
         print("\n".join(logs))

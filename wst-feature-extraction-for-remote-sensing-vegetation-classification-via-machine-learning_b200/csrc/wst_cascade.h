@@ -43,8 +43,18 @@ constexpr int kMaxJ = 6;
 constexpr int kMaxL = 8;                 // orientations per scale supported by the compiled cascades
 constexpr int kMaxPairs = kMaxJ * (kMaxJ - 1) / 2;
 WST_CX int pair_index(int j2, int j1) { return j2 * (j2 - 1) / 2 + j1; }
-constexpr int kSmemCfloats = 27000;      // data region budget (216,000 B) of the 227 KB a CTA may use
-constexpr int kGlobalCfloats = 1 << 24;  // data region budget of the global-workspace variant (128 MiB per CTA, never reached)
+#ifndef WST_SMEM_BUDGET
+#define WST_SMEM_BUDGET 27000
+#endif
+constexpr int kSmemCfloats = WST_SMEM_BUDGET;   // data region budget: 216,000 B of the 227 KB a CTA may use by default;
+                                                // smaller for configurations that run several CTAs per SM
+#ifndef WST_GLOBAL_BUDGET
+#define WST_GLOBAL_BUDGET (1 << 24)
+#endif
+// Data region budget of the global-workspace variant, in cfloats.  It sets how many same-scale arrays are processed
+// together (GP, G2) and therefore the hot working set of one signal; the cluster variant picks it so that the working
+// sets of all signals in flight stay resident in L2.
+constexpr int kGlobalCfloats = WST_GLOBAL_BUDGET;
 
 // ------------------------------------------------------------------ 1-D factorisation n = R1*R2
 // Prime-factor (Good-Thomas) split n = P * Q with P the power-of-two part and Q the odd part: the two passes
@@ -129,10 +139,16 @@ WST_CX bool lp_banded(int m, int hout, int level) {
 // WS_GLOBAL = false: the data region lives in shared memory (the fast path, N <= 160).
 // WS_GLOBAL = true : same program, data region in a per-CTA global-memory workspace — correct for sides whose
 //                    spectra exceed one SM's shared memory (512x512 J=5 -> 576), not yet tuned.
-template <int N_, int J_, int NT_ = WST_NT, bool WS_GLOBAL_ = false>
+// CL > 1 (global-workspace variant only): one signal is processed by a thread-block cluster of CL CTAs.  NT is the
+//                    number of threads of the whole cluster (the stride of every phase loop), NTL = NT / CL the
+//                    threads of one CTA; a phase ends with a cluster barrier instead of __syncthreads(), every CTA
+//                    keeps its own copy of the twiddle / low-pass tables in shared memory, and the low-pass reduction
+//                    buffer moves from shared memory to the workspace.
+template <int N_, int J_, int NT_ = WST_NT, bool WS_GLOBAL_ = false, int CL_ = 1>
 struct Cfg {
-    static constexpr int N = N_, J = J_, NT = NT_;
+    static constexpr int N = N_, J = J_, NT = NT_, CL = CL_, NTL = NT_ / CL_;
     static constexpr bool WS_GLOBAL = WS_GLOBAL_;
+    static_assert(CL_ >= 1 && NT_ % CL_ == 0 && (CL_ == 1 || WS_GLOBAL_), "clusters need the global-workspace variant");
     static constexpr int BUDGET = WS_GLOBAL_ ? kGlobalCfloats : kSmemCfloats;
     static constexpr int NS = N >> J;           // side of the subsampled (still padded) output grid
     static constexpr int HOUT = NS - 2;         // kept outputs per side after unpad [1:-1]
@@ -213,9 +229,19 @@ struct Cfg {
     // bytes of dynamic shared memory, and of per-CTA global workspace (0 for the shared-memory variant)
     static WST_CX size_t smem_bytes() {
         return (size_t)((WS_GLOBAL ? 0 : smem_cfloats()) + tw_total) * sizeof(cfloat)
-               + (size_t)(g_total + lpbuf_floats()) * sizeof(float);
+               + (size_t)(g_total + (CL > 1 ? 0 : lpbuf_floats())) * sizeof(float);
     }
-    static WST_CX size_t workspace_cfloats() { return WS_GLOBAL ? (size_t)smem_cfloats() : 0; }
+    // CTAs meant to share an SM (small configurations run several narrower CTAs, so that one CTA's barrier waits are
+    // filled by another's work): bounded by shared memory and by keeping 640 threads' worth of registers per SM.
+    static WST_CX int min_ctas() {
+        if (CL > 1) return 1;
+        int by_smem = (int)(232448 / (smem_bytes() + 1024)), by_threads = (WS_GLOBAL ? 512 : 640) / NTL;
+        int m = by_smem < by_threads ? by_smem : by_threads;
+        return m < 1 ? 1 : m;
+    }
+    static WST_CX size_t workspace_cfloats() {
+        return WS_GLOBAL ? (size_t)smem_cfloats() + (CL > 1 ? (size_t)(lpbuf_floats() + 1) / 2 : 0) : 0;
+    }
     static_assert(level_total(0, 1) <= BUDGET, "padded size too large for the shared-memory cascade");
 };
 
@@ -292,16 +318,30 @@ enum PhaseKind { PK_TWIDDLE = 0, PK_INPUT, PK_LP1, PK_LP2, PK_RFFT_ROW_S, PK_RFF
 constexpr int kNumPhaseTags = PK_COUNT * 8;
 
 #ifdef __CUDACC__
-struct DevExec {
-    template <int TAG, class F> WST_D void phase(F&& f) { f((int)threadIdx.x); __syncthreads(); }
+// Barrier closing a phase: the CTA's, or the cluster's (release/acquire at cluster scope, so workspace writes of
+// one CTA are visible to the others afterwards).
+template <int CL> WST_D void phase_barrier() {
+    if constexpr (CL > 1) {
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    } else {
+        __syncthreads();
+    }
+}
+WST_D int cluster_cta_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return (int)r; }
+// `base` = rank of this CTA in its cluster * threads per CTA (0 without clusters): phase lambdas see the thread's
+// index within the whole group that works on the signal.
+template <int CL> struct DevExec {
+    int base;
+    template <int TAG, class F> WST_D void phase(F&& f) { f(base + (int)threadIdx.x); phase_barrier<CL>(); }
 };
 // Accumulates, per tag, the cycles from phase entry to barrier release as seen by thread 0.
-struct ProfExec {
+template <int CL> struct ProfExec {
+    int base;
     long long* acc;    // shared memory, kNumPhaseTags entries
     template <int TAG, class F> WST_D void phase(F&& f) {
         long long t0 = clock64();
-        f((int)threadIdx.x);
-        __syncthreads();
+        f(base + (int)threadIdx.x);
+        phase_barrier<CL>();
         if (threadIdx.x == 0) acc[TAG] += clock64() - t0;
     }
 };
@@ -754,10 +794,10 @@ WST_D void lowpass_maps_dense(Exec& ex, cfloat* z, int ZS, int narr, const float
                     constexpr int k = decltype(Q)::value;
                     const float4 a = *reinterpret_cast<const float4*>(g0 + x * HP + 4 * k);
                     const float4 d = *reinterpret_cast<const float4*>(g0 + (x + HALF) * HP + 4 * k);
-                    acc[4 * k + 0] += a.x * v.x + d.x * v.y;
-                    acc[4 * k + 1] += a.y * v.x + d.y * v.y;
-                    acc[4 * k + 2] += a.z * v.x + d.z * v.y;
-                    acc[4 * k + 3] += a.w * v.x + d.w * v.y;
+                    acc[4 * k + 0] += a.x * v.x; acc[4 * k + 0] += d.x * v.y;      // two FMAs (a sum of products first
+                    acc[4 * k + 1] += a.y * v.x; acc[4 * k + 1] += d.y * v.y;      // would cost a multiply, an FMA and an add)
+                    acc[4 * k + 2] += a.z * v.x; acc[4 * k + 2] += d.z * v.y;
+                    acc[4 * k + 3] += a.w * v.x; acc[4 * k + 3] += d.w * v.y;
                 });
             }
             float* tp = reinterpret_cast<float*>(z + g * ZS + HALF * P) + y * PT + q * GO1;
@@ -929,8 +969,9 @@ struct Cascade {
             static_for<0, J>([&](auto Jj) {
                 constexpr int j = decltype(Jj)::value;
                 constexpr int m = C::msize(j);
-                for (int i = tid; i < m; i += NT) twsm[C::tw_offset(j) + i] = pt.tw[j][i];
-                for (int i = tid; i < m * HP; i += NT) gsm[C::g_offset(j) + i] = pt.gr[j][i];
+                const int lt = tid % C::NTL;      // every CTA of a cluster fills its own copy of the tables
+                for (int i = lt; i < m; i += C::NTL) twsm[C::tw_offset(j) + i] = pt.tw[j][i];
+                for (int i = lt; i < m * HP; i += C::NTL) gsm[C::g_offset(j) + i] = pt.gr[j][i];
             });
         });
     }

@@ -1,5 +1,7 @@
 // wst_cfg_inst.cu — one compiled cascade configuration: compile with -DWST_CFG_N=<padded side> -DWST_CFG_J=<J>
-// (and -DWST_CFG_GLOBAL=1 -DWST_CFG_NT=<threads> for the global-workspace variant).
+// (and -DWST_CFG_GLOBAL=1 -DWST_CFG_NT=<threads> for the global-workspace variant; -DWST_CFG_CL=<CTAs per cluster>
+// -DWST_GLOBAL_BUDGET=<cfloats> to spread one signal over a thread-block cluster, WST_CFG_NT then counts the threads
+// of the whole cluster).
 #include "wst_ops.h"
 
 #ifndef WST_CFG_GLOBAL
@@ -8,75 +10,126 @@
 #ifndef WST_CFG_NT
 #define WST_CFG_NT WST_NT
 #endif
+#ifndef WST_CFG_CL
+#define WST_CFG_CL 1
+#endif
 
 using namespace wst;
 
 namespace {
 
-typedef Cfg<WST_CFG_N, WST_CFG_J, WST_CFG_NT, (WST_CFG_GLOBAL != 0)> ThisCfg;
+typedef Cfg<WST_CFG_N, WST_CFG_J, WST_CFG_NT, (WST_CFG_GLOBAL != 0), WST_CFG_CL> ThisCfg;
 
 template <class C, class Exec>
 __device__ __forceinline__ void run_cascade(Exec& ex, const PlanTables& pt, const InputDesc& in,
                                             long long nsig, cfloat* u0h_scratch, cfloat* workspace, float* maps_out,
                                             float* maps_scratch, float* feats) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    // slot = the CTA (or cluster of C::CL CTAs) that owns one signal at a time; its scratch areas are indexed by it
+    const int slot = blockIdx.x / C::CL, nslots = gridDim.x / C::CL;
     cfloat* sbase = reinterpret_cast<cfloat*>(smem_raw);
-    cfloat* sm = C::WS_GLOBAL ? workspace + (size_t)blockIdx.x * C::workspace_cfloats() : sbase;
+    cfloat* sm = C::WS_GLOBAL ? workspace + (size_t)slot * C::workspace_cfloats() : sbase;
     cfloat* twsm = C::WS_GLOBAL ? sbase : sbase + C::smem_cfloats();
     float* gsm = reinterpret_cast<float*>(twsm + C::tw_total);
-    float* lpbuf = gsm + C::g_total;
+    float* lpbuf = C::CL > 1 ? reinterpret_cast<float*>(sm + C::smem_cfloats()) : gsm + C::g_total;
     const size_t map_elems = (size_t)pt.K * C::HOUT * C::HOUT;
     Cascade<C, Exec> prog{ex, pt, sm, twsm, gsm, lpbuf,
-                          u0h_scratch + (size_t)blockIdx.x * (C::N * (C::N / 2 + 1)), nullptr};
+                          u0h_scratch + (size_t)slot * (C::N * (C::N / 2 + 1)), nullptr};
     prog.load_twiddles();
-    for (long long s = blockIdx.x; s < nsig; s += gridDim.x) {
-        // maps go to the caller's buffer, or to this CTA's own (L2-resident) scratch when only features are wanted
-        prog.maps = maps_out ? maps_out + (size_t)s * map_elems : maps_scratch + (size_t)blockIdx.x * map_elems;
+    for (long long s = slot; s < nsig; s += nslots) {
+        // maps go to the caller's buffer, or to this slot's own (L2-resident) scratch when only features are wanted
+        prog.maps = maps_out ? maps_out + (size_t)s * map_elems : maps_scratch + (size_t)slot * map_elems;
         const SignalSrc src = signal_source(in, s, pt.H, pt.W);
         prog.run(src, feats ? feats + (size_t)s * 2 * pt.K : nullptr);
     }
 }
 
-// One persistent CTA per SM; each CTA runs the whole scattering cascade of one (patch, channel) signal at a
-// time (wst_cascade.h).
+// One persistent CTA per SM; each CTA (or each cluster of C::CL CTAs, for sides whose arrays live in the L2-resident
+// workspace) runs the whole scattering cascade of one (patch, channel) signal at a time (wst_cascade.h).
 template <class C>
-__global__ void __launch_bounds__(C::NT, 1)
+__global__ void __launch_bounds__(C::NTL, C::min_ctas())
 cascade_kernel(const PlanTables pt, const InputDesc in, long long nsig, cfloat* u0h_scratch,
                cfloat* workspace, float* maps_out, float* maps_scratch, float* feats) {
-    DevExec ex;
+    DevExec<C::CL> ex{C::CL > 1 ? cluster_cta_rank() * C::NTL : 0};
     run_cascade<C>(ex, pt, in, nsig, u0h_scratch, workspace, maps_out, maps_scratch, feats);
 }
 
 // Debug twin: same program, executor that accumulates clock64() per phase tag; CTA 0's totals -> cycles.
 template <class C>
-__global__ void __launch_bounds__(C::NT, 1)
+__global__ void __launch_bounds__(C::NTL, 1)
 cascade_prof_kernel(const PlanTables pt, const InputDesc in, long long nsig, cfloat* u0h_scratch,
                     cfloat* workspace, float* maps_out, float* maps_scratch, float* feats, long long* cycles) {
     __shared__ long long acc[kNumPhaseTags];
-    for (int i = threadIdx.x; i < kNumPhaseTags; i += C::NT) acc[i] = 0;
+    for (int i = threadIdx.x; i < kNumPhaseTags; i += C::NTL) acc[i] = 0;
     __syncthreads();
-    ProfExec ex{acc};
+    ProfExec<C::CL> ex{C::CL > 1 ? cluster_cta_rank() * C::NTL : 0, acc};
     run_cascade<C>(ex, pt, in, nsig, u0h_scratch, workspace, maps_out, maps_scratch, feats);
     if (blockIdx.x == 0)
-        for (int i = threadIdx.x; i < kNumPhaseTags; i += C::NT) cycles[i] = acc[i];
+        for (int i = threadIdx.x; i < kNumPhaseTags; i += C::NTL) cycles[i] = acc[i];
+}
+
+// `slots` = CTAs (clusters) to launch; the grid is slots * C::CL CTAs of C::NTL threads.
+template <class C, class... Args>
+cudaError_t launch_any(void (*kernel)(Args...), int slots, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(slots * C::CL), 1, 1);
+    cfg.blockDim = dim3(C::NTL, 1, 1);
+    cfg.dynamicSmemBytes = C::smem_bytes();
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C::CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = C::CL > 1 ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
 template <class C>
 cudaError_t launch_cascade(const PlanTables& pt, const InputDesc& in, long long nsig, cfloat* u0h, cfloat* ws,
-                           float* maps_out, float* maps_scratch, float* feats, int grid, cudaStream_t st) {
-    cascade_kernel<C><<<grid, C::NT, C::smem_bytes(), st>>>(pt, in, nsig, u0h, ws, maps_out, maps_scratch, feats);
-    return cudaGetLastError();
+                           float* maps_out, float* maps_scratch, float* feats, int slots, cudaStream_t st) {
+    return launch_any<C>(cascade_kernel<C>, slots, st, pt, in, nsig, u0h, ws, maps_out, maps_scratch, feats);
 }
 
 template <class C>
 cudaError_t launch_cascade_prof(const PlanTables& pt, const InputDesc& in, long long nsig, cfloat* u0h, cfloat* ws,
-                                float* maps_out, float* maps_scratch, float* feats, long long* cycles, int grid,
+                                float* maps_out, float* maps_scratch, float* feats, long long* cycles, int slots,
                                 cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(cascade_prof_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)C::smem_bytes());
+    if (e == cudaSuccess && C::CL > 8)
+        e = cudaFuncSetAttribute(cascade_prof_kernel<C>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) return e;
-    cascade_prof_kernel<C><<<grid, C::NT, C::smem_bytes(), st>>>(pt, in, nsig, u0h, ws, maps_out, maps_scratch, feats, cycles);
-    return cudaGetLastError();
+    return launch_any<C>(cascade_prof_kernel<C>, slots, st, pt, in, nsig, u0h, ws, maps_out, maps_scratch, feats, cycles);
+}
+
+// Signals in flight: resident CTAs, or resident clusters (the hardware places a cluster inside one GPC).
+template <class C>
+cudaError_t max_slots(int device, int* slots) {
+    cudaError_t e = cudaFuncSetAttribute(cascade_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes());
+    if (e != cudaSuccess) return e;
+    int sms = 0;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) return e;
+    if (C::CL == 1) {
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cascade_kernel<C>, C::NTL, C::smem_bytes());
+        *slots = sms * per_sm;
+        return e;
+    }
+    if (C::CL > 8) {
+        e = cudaFuncSetAttribute(cascade_kernel<C>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return e;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(sms / C::CL * C::CL), 1, 1);
+    cfg.blockDim = dim3(C::NTL, 1, 1);
+    cfg.dynamicSmemBytes = C::smem_bytes();
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C::CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaOccupancyMaxActiveClusters(slots, cascade_kernel<C>, &cfg);
 }
 
 }  // namespace
@@ -89,7 +142,7 @@ wst::CfgOps WST_CAT(wst_make_ops_, WST_CFG_N, _, WST_CFG_J)() {
     static_assert(C::smem_bytes() + kNumPhaseTags * 8 <= 232448,
                   "configuration exceeds the 227 KB of shared memory a CTA may use");
     CfgOps o;
-    o.N = C::N; o.J = C::J; o.NT = C::NT; o.hout = C::HOUT;
+    o.N = C::N; o.J = C::J; o.NT = C::NT; o.hout = C::HOUT; o.cluster = C::CL;
     o.smem = C::smem_bytes();
     o.workspace_cfloats = C::workspace_cfloats();
     o.kernel = (const void*)cascade_kernel<C>;
@@ -97,5 +150,6 @@ wst::CfgOps WST_CAT(wst_make_ops_, WST_CFG_N, _, WST_CFG_J)() {
     o.bind = &bind_tables<C>;
     o.launch = &launch_cascade<C>;
     o.launch_prof = &launch_cascade_prof<C>;
+    o.max_slots = &max_slots<C>;
     return o;
 }

@@ -310,16 +310,14 @@ int wst2d_plan_create(wst2d_plan** out, int device, int H, int W, int J, int L, 
     p->pt.H = H; p->pt.W = W; p->pt.pad_top = (Hp - H) / 2; p->pt.pad_left = (Wp - W) / 2;
     ops->bind(p->pt, p->d_tables, off);
 
-    e = cudaFuncSetAttribute(ops->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ops->smem);
-    int per_sm = 0, sms = 0;
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ops->kernel, ops->NT, ops->smem);
-    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    if (e != cudaSuccess || per_sm < 1) {
-        std::string m = e != cudaSuccess ? cudaGetErrorString(e) : "kernel does not fit on an SM";
+    int slots = 0;
+    e = ops->max_slots(device, &slots);
+    if (e != cudaSuccess || slots < 1) {
+        std::string m = e != cudaSuccess ? cudaGetErrorString(e) : "kernel does not fit on the device";
         cudaFree(p->d_tables); delete p;
         return fail(WST2D_ERR_CUDA, "cascade kernel setup: " + m);
     }
-    p->grid_max = sms * per_sm;
+    p->grid_max = slots;
     {   // keep the stream-ordered scratch (cudaMallocAsync in forward) cached across synchronisations
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {

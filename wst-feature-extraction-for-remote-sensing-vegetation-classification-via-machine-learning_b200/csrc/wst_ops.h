@@ -11,13 +11,15 @@ namespace wst {
 
 struct CfgOps {
     int N, J, NT, hout;
+    int cluster;                 // CTAs per signal (1: one CTA per signal; > 1: a thread-block cluster per signal)
     size_t smem;                 // dynamic shared memory per CTA
-    size_t workspace_cfloats;    // per-CTA global workspace (0: data region in shared memory)
+    size_t workspace_cfloats;    // per-slot global workspace (0: data region in shared memory)
     const void* kernel;
     bool (*build)(int, const float*, const float*, std::vector<float>&, TableOffsets&, std::string&);
     void (*bind)(PlanTables&, const float*, const TableOffsets&);
     // (tables, input descriptor, nsig, u0h scratch, workspace, maps_out | NULL, per-CTA maps scratch | NULL, feats | NULL, grid, stream)
     cudaError_t (*launch)(const PlanTables&, const InputDesc&, long long, cfloat*, cfloat*, float*, float*, float*, int, cudaStream_t);
+    cudaError_t (*max_slots)(int device, int* slots);   // signals in flight (resident CTAs or clusters); also sets kernel attributes
     cudaError_t (*launch_prof)(const PlanTables&, const InputDesc&, long long, cfloat*, cfloat*, float*, float*, float*, long long*, int, cudaStream_t);
 };
 
