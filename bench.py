@@ -290,12 +290,20 @@ def run_ours(args, cfg):
         avg_launch_ms = cas_ms / cas_n if cas_n else float("nan")
         patches_per_launch = B / launches_per_step if launches_per_step else 0
         achieved = bytes_min * patches_per_launch / (avg_launch_ms * 1e-3) / 1e9
-        traffic = None
+        # DRAM bytes of one launch, from the committed ncu --set full capture of this kernel (profiles/): the kernel is
+        # persistent and its traffic is per signal, so a capture of a different batch is scaled to this launch's batch
+        traffic, traffic_note = None, None
         prof_json = os.path.join(ROOT, "profiles", "ncu_cascade_%s.json" % args.config)
-        if os.path.exists(prof_json):
+        if os.path.exists(prof_json) and patches_per_launch:
             pj = json.load(open(prof_json))
-            if pj.get("patches_per_launch") == patches_per_launch:
-                traffic = pj.get("dram_bytes_per_launch")
+            traffic = pj["dram_bytes_per_launch"] * patches_per_launch / pj["patches_per_launch"]
+            traffic_note = "%s: %d patches captured, scaled to %d" % (pj.get("source", prof_json), pj["patches_per_launch"], patches_per_launch)
+        dram_gbs = traffic / (avg_launch_ms * 1e-3) / 1e9 if traffic else None
+        on_chip = traffic is not None and traffic < 2 * bytes_min * patches_per_launch
+        note = ("HBM sees the input and the features once (traffic ~ algorithmic bytes); the fused path is fp32 / shared-memory "
+                "bound (SURVEY.md F3), see fp32" if on_chip or traffic is None else
+                "data region of this side lives in a global workspace: the kernel streams it through HBM (dram_achieved), "
+                "traffic >> algorithmic bytes")
         fl = flops_model(M, J, L, C)
         try:
             fma_peak = wst_b200.fma_peak_tflops(local)
@@ -319,8 +327,9 @@ def run_ours(args, cfg):
                          "frac": round(achieved / hbm_peak, 6), "traffic": traffic, "peak_source": peak_src,
                          "kernel": "cascade_kernel", "kernel_ms_per_launch": round(avg_launch_ms, 4),
                          "kernel_share_of_step": round(cas_ms / ms, 4) if ms else None,
-                         "algorithmic_bytes_per_patch": bytes_min,
-                         "note": "fused path is fp32/shared-memory bound (SURVEY.md F3); see fp32"},
+                         "algorithmic_bytes_per_patch": bytes_min, "traffic_source": traffic_note,
+                         "dram_achieved": round(dram_gbs, 1) if dram_gbs else None,
+                         "dram_frac": round(dram_gbs / hbm_peak, 4) if dram_gbs else None, "note": note},
             "fp32": {"model_flops_per_patch": fl, "achieved_tflops": round(value / world * fl / 1e12, 3),
                      "peak_tflops": round(fma_peak, 2) if fma_peak else None,
                      "frac": round(value / world * fl / 1e12 / fma_peak, 4) if fma_peak else None,
