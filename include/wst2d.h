@@ -78,7 +78,7 @@ int wst2d_forward_scene(const wst2d_plan* plan, const float* raster_dev, int C, 
  * src/training/train_and_save_model.py:58-112 = src/inference/inference.py:181-235), 18 statistics per channel
  * in the reference's order: mean std var min max range skew kurt cv p10 p25 p50 p75 p90 iqr mad grad_mean
  * edge_density.  x_dev: float32 [B][C][H][W], or uint8 [B][H][W][C] when is_u8 != 0; out_dev: float32
- * [B][C][18].  Needs no plan.  H*W (rounded up to a power of two for the sort) must fit in shared memory
+ * [B][C][18].  Needs no plan.  The image and its |laplace| map (2*H*W floats) must fit in shared memory
  * (128x128 does); inputs are assumed finite (the reference drops non-finite pixels).  Errors are reported by
  * wst2d_advanced_stats_last_error(). */
 int wst2d_advanced_stats(int device, const void* x_dev, int is_u8, int64_t B, int C, int H, int W,

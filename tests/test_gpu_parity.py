@@ -130,6 +130,21 @@ def test_cfg5_512_J5_multispectral(wst):
     assert torch.equal(f1[0, 0], feats[0, 3])
 
 
+@pytest.mark.parametrize("J,N,h", [(2, 264, 64), (3, 272, 32), (4, 288, 16)])
+def test_256x256_patches(wst, J, N, h):
+    """256x256 patches (padded sides 264 = 22*12, 272 = 16*17, 288 = 16*18) run through the global-workspace cascade."""
+    rng = np.random.default_rng(100 + J)
+    x = (rng.integers(0, 256, (3, 1, 256, 256)) / 255.0).astype(np.float32)
+    plan = wst.get_plan(256, 256, J, 8)
+    assert (plan.h, plan.Hp) == (h, N)
+    feats, maps = plan.forward(torch.from_numpy(x).cuda(), True, True)
+    ref = oracle64(256, J, 8)(x[:2, 0])
+    assert floored_rel(maps[:2, 0].cpu().numpy().reshape(2, -1), ref.reshape(2, -1)) <= TOL
+    f = feats[:2, 0].cpu().numpy()
+    assert floored_rel(f[:, 0], ref.mean(axis=(-2, -1))) <= TOL
+    assert floored_rel(f[:, 1], ref.std(axis=(-2, -1))) <= TOL
+
+
 def test_max_order_1(wst):
     x = torch.rand(2, 1, 32, 32, device="cuda")
     p1, p2 = wst.get_plan(32, 32, 2, 8, 1), wst.get_plan(32, 32, 2, 8, 2)
