@@ -32,6 +32,7 @@ int run_cfg(int L, int max_order, int H, int W, const float* psi_hat, const floa
     bind_tables<C>(pt, buf.data(), off);
     std::vector<cfloat> sm(C::smem_cfloats() + 64), twsm(C::tw_total);
     std::vector<float> gsm(C::g_total), lpbuf(C::lpbuf_floats() + 1);
+    std::vector<cfloat> stage(C::stage_cfloats() + 1);
     std::vector<cfloat> u0h((size_t)C::N * (C::N / 2 + 1));
     HostExec<C::NT> ex;
     const size_t map_sz = (size_t)pt.K * C::HOUT * C::HOUT;
@@ -39,7 +40,7 @@ int run_cfg(int L, int max_order, int H, int W, const float* psi_hat, const floa
         // poison shared memory so that reads of never-written cells show up as NaN
         for (auto& v : sm) v = cmake(NAN, NAN);
         for (auto& v : lpbuf) v = NAN;
-        Cascade<C, HostExec<C::NT>> prog{ex, pt, sm.data(), twsm.data(), gsm.data(), lpbuf.data(), u0h.data(), maps_out + s * map_sz};
+        Cascade<C, HostExec<C::NT>> prog{ex, pt, sm.data(), twsm.data(), gsm.data(), lpbuf.data(), stage.data(), u0h.data(), maps_out + s * map_sz};
         prog.load_twiddles();
         SignalSrc src{x + (size_t)s * H * W, nullptr, 1, W};
         prog.run(src, feats_out ? feats_out + (size_t)s * 2 * pt.K : nullptr);

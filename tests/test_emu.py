@@ -121,3 +121,35 @@ def test_shipped_build_variants_vs_oracle(tmp_path):
         ref = S(x)
         assert not np.isnan(out).any() and floored_rel(out, ref) <= 1e-4 / 4
         assert floored_rel(feats[:, 0], ref.mean(axis=(-2, -1))) <= 1e-4 / 4
+
+
+def test_global_workspace_variant_vs_oracle(tmp_path):
+    """The global-workspace variant of the cascade (sides whose arrays exceed shared memory: 256x256, 512x512) runs its
+    inverse FFTs on staged shared-memory tiles.  Replayed here at small sides, where the oracle is quick: fused and
+    unfused low-pass, Cooley-Tukey and Good-Thomas lengths, single-pass levels."""
+    import ctypes
+    import subprocess
+    inc = tmp_path / "glob_configs.inc"
+    inc.write_text("CFGG(40, 2)\nCFGG(80, 3)\nCFGG(136, 2)\nCFGG(48, 3)\n")
+    lib_path = tmp_path / "libwst_emu_glob.so"
+    subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-DWST_GLOBAL_BUDGET=32768",
+                    "-DWST_EMU_CONFIG_FILE=\"%s\"" % inc.name, "-I", str(tmp_path), "-I", emu.CSRC, "-I", emu.HERE,
+                    emu.HERE + "/wst_emu.cpp", "-o", str(lib_path)], check=True)
+    lib = ctypes.CDLL(str(lib_path))
+    lib.emu_forward.argtypes = [ctypes.c_int] * 6 + [ctypes.c_void_p] * 3 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    for M, J, L, N in [(32, 2, 8, 40), (64, 3, 8, 80), (128, 2, 8, 136), (32, 3, 6, 48)]:
+        rng = np.random.default_rng(N)
+        x = (rng.integers(0, 256, (2, M, M)) / 255.0).astype(np.float32)
+        S = Scattering2D(J=J, shape=(M, M), L=L, precision="double", cache_filters=True)
+        assert S._M_padded == N
+        psi = np.ascontiguousarray(np.stack([p["levels"][0] for p in S.psi]), np.float32)
+        phi = np.ascontiguousarray(S.phi["levels"][0], np.float32)
+        ref = S(x)
+        K, h = ref.shape[1], N // 2 ** J - 2
+        out = np.full((2, K, h, h), np.nan, np.float32)
+        feats = np.full((2, 2, K), np.nan, np.float32)
+        rc = lib.emu_forward(N, J, L, 2, M, M, psi.ctypes.data, phi.ctypes.data, x.ctypes.data, 2, out.ctypes.data,
+                             feats.ctypes.data)
+        assert rc == 0
+        assert not np.isnan(out).any() and floored_rel(out, ref) <= 1e-4 / 4, (M, J)
+        assert floored_rel(feats[:, 0], ref.mean(axis=(-2, -1))) <= 1e-4 / 4

@@ -174,7 +174,7 @@ class Plan:
         self._check_x(x)
         kinds = ["twiddle", "input", "lp1", "lp2", "rfft_row_s", "rfft_row_c", "rfft_split", "rfft_col_s",
                  "rfft_col_c", "u0_store", "prod1", "prod2", "ifft_col_c", "ifft_col_s", "ifft_row_c", "ifft_final",
-                 "lp_reduce", "lp_store", "pool"]
+                 "lp_reduce", "lp_store", "pool", "stage_load", "stage_store"]
         n = 8 * len(kinds)
         arr = (ctypes.c_int64 * n)()
         _lib.check(_lib.load().wst2d_debug_phase_cycles(self._h, x.data_ptr(), x.shape[0] * x.shape[1], arr, n))

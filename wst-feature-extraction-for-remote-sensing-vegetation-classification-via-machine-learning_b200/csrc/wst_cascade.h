@@ -228,8 +228,17 @@ struct Cfg {
     static WST_CX int lpbuf_floats() { return any_fused() ? LP_SLOTS * HOUT * HOUT : 0; }
     // bytes of dynamic shared memory, and of per-CTA global workspace (0 for the shared-memory variant)
     static WST_CX size_t smem_bytes() {
-        return (size_t)((WS_GLOBAL ? 0 : smem_cfloats()) + tw_total) * sizeof(cfloat)
+        return (size_t)((WS_GLOBAL ? 0 : smem_cfloats()) + tw_total + stage_cfloats()) * sizeof(cfloat)
                + (size_t)(g_total + (CL > 1 ? 0 : lpbuf_floats())) * sizeof(float);
+    }
+    // Global-workspace variant: the passes of an inverse FFT run on shared-memory tiles (a batch of columns, then a
+    // batch of row pairs) so that each array crosses HBM once per dimension instead of once per pass.
+    static WST_CX int stage_cols(int m) { int t = 16; while (m % t) t /= 2; return t; }          // columns per tile
+    static WST_CX int stage_cfloats() { return WS_GLOBAL ? N * (stage_cols(N) + 1) : 0; }      // one level-0 column tile
+    static WST_CX int stage_rows(int m) {                                                       // row pairs per tile
+        int t = 16;
+        while (t > 1 && ((m / 2) % t != 0 || 2 * t * (m + 1) > stage_cfloats())) t /= 2;
+        return t;
     }
     // CTAs meant to share an SM (small configurations run several narrower CTAs, so that one CTA's barrier waits are
     // filled by another's work): bounded by shared memory and by keeping 640 threads' worth of registers per SM.
@@ -314,7 +323,7 @@ WST_D SignalSrc signal_source(const InputDesc& in, long long s, int H, int W) {
 // executor of the debug entry point; the production executor ignores them.
 enum PhaseKind { PK_TWIDDLE = 0, PK_INPUT, PK_LP1, PK_LP2, PK_RFFT_ROW_S, PK_RFFT_ROW_C, PK_RFFT_SPLIT,
                  PK_RFFT_COL_S, PK_RFFT_COL_C, PK_U0_STORE, PK_PROD1, PK_PROD2, PK_IFFT_COL_C, PK_IFFT_COL_S,
-                 PK_IFFT_ROW_C, PK_IFFT_FINAL, PK_LPR, PK_LPS, PK_POOL, PK_COUNT };
+                 PK_IFFT_ROW_C, PK_IFFT_FINAL, PK_LPR, PK_LPS, PK_POOL, PK_STAGE_LD, PK_STAGE_ST, PK_COUNT };
 constexpr int kNumPhaseTags = PK_COUNT * 8;
 
 #ifdef __CUDACC__
@@ -435,9 +444,12 @@ WST_D void fft_lines_inv(Exec& ex, cfloat* base, int narr, int AS, const cfloat*
 //              no z :  row r, column slot (q*R2 + i2) <- (acc_r[2q], acc_r[2q+1]),  q < HOUT/2
 //              z    :  row x+M/2, slot (q*R2 + i2) <- acc_x[..],  slot ((HOUT/2+q)*R2 + i2) <- acc_{x+M/2}[..]
 //            (single-pass lengths hold whole rows: the slot is column q and the sum over y is complete).
-template <int M, int NT, bool WRITE_Z, bool LPF, int HOUT, int HP, bool SUBFAST = false>
+//   XN, POFF: rows x < XN are paired with the rows POFF elements further on (the whole array: M/2 and M/2 rows; a
+//            staged tile of the global-workspace variant: its row pairs, stored top half then bottom half).
+template <int M, int NT, bool WRITE_Z, bool LPF, int HOUT, int HP, bool SUBFAST = false, int XN = M / 2,
+          int POFF = (M / 2) * (M + 1)>
 WST_D void pass_rows_final(int tid, cfloat* base, int narr, int AS, const float* gc) {
-    constexpr int R1 = Fft1<M>::R1, R2 = Fft1<M>::R2, P = M + 1, HALF = M / 2;
+    constexpr int R1 = Fft1<M>::R1, R2 = Fft1<M>::R2, P = M + 1, HALF = XN;
     constexpr int NV = (R1 > 1) ? R1 : R2;            // values per row held by one thread
     constexpr int YS = (R1 > 1) ? R2 : 1;             // their stride along y
     const int nsub = (R1 > 1) ? R2 : 1;
@@ -447,7 +459,7 @@ WST_D void pass_rows_final(int tid, cfloat* base, int narr, int AS, const float*
         if constexpr (SUBFAST) { i2 = b % nsub; int r = b / nsub; x = r % HALF; g = r / HALF; }
         else { x = b % HALF; int r = b / HALF; i2 = r % nsub; g = r / nsub; }
         cfloat* p0 = base + g * AS + x * P + i2;
-        cfloat* p1 = p0 + HALF * P;
+        cfloat* p1 = p0 + POFF;
         cfloat a[NV], c[NV];
         static_for<0, NV>([&](auto K) { constexpr int k = decltype(K)::value; a[k] = p0[k * YS]; c[k] = p1[k * YS]; });
         dft<NV, +1>(a);
@@ -918,14 +930,107 @@ WST_D void lowpass_maps(Exec& ex, cfloat* z, int ZS, int narr, const float* gr, 
     else lowpass_maps_dense<M, HOUT, HP, NT, LV>(ex, z, ZS, narr, gr, gc, maps, coef);
 }
 
+// Tile loads of the staged passes: asynchronous 8-byte global -> shared copies (LDGSTS), so that a thread's whole
+// share of the tile is in flight at once instead of one register round trip after another; stage_copy_wait() closes the
+// phase that issued them.  (Host emulation: plain copies.)
+WST_D void stage_copy(cfloat* dst_shared, const cfloat* src_global) {
+#ifdef __CUDA_ARCH__
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_shared);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src_global) : "memory");
+#else
+    *dst_shared = *src_global;
+#endif
+}
+WST_D void stage_copy_wait() {
+#ifdef __CUDA_ARCH__
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+
+// Global-workspace variant: both passes of the inverse column transforms on shared-memory tiles of TC columns (all M
+// rows; as many arrays per tile batch as the stage holds), then the row pass and the final pass (modulus, pairing,
+// first low-pass contraction) on tiles of TR row pairs.  An array is read and written once per dimension instead of
+// once per pass; tile loads and stores move 8*TC-byte / whole-row segments.
+template <int M, int NT, int STAGE, int LV, class Exec>
+WST_D void ifft_cols_staged(Exec& ex, cfloat* base, int narr, int AS, const cfloat* tw, cfloat* stage) {
+    constexpr int P = M + 1, TC = (M % 16 == 0) ? 16 : (M % 8 == 0) ? 8 : (M % 4 == 0) ? 4 : 2, TCP = TC + 1, TILE = M * TCP;
+    constexpr int NAB = STAGE / TILE;
+    static_assert(NAB >= 1, "stage too small for a column tile");
+    for (int g0 = 0; g0 < narr; g0 += NAB) {
+        const int na = narr - g0 < NAB ? narr - g0 : NAB;
+        for (int c0 = 0; c0 < M; c0 += TC) {
+            ex.template phase<PK_STAGE_LD * 8 + LV>([&](int tid) {
+                for (int i = tid; i < na * M * TC; i += NT) {
+                    const int c = i % TC, r = (i / TC) % M, a = i / (TC * M);
+                    stage_copy(stage + a * TILE + r * TCP + c, base + (g0 + a) * AS + r * P + c0 + c);
+                }
+                stage_copy_wait();
+            });
+            ex.template phase<PK_IFFT_COL_C * 8 + LV>([&](int tid) { pass_contig<M, +1, true, TC, 1, TCP, NT>(tid, stage, na, TILE, tw); });
+            if constexpr (Fft1<M>::R1 > 1) {
+                ex.template phase<PK_IFFT_COL_S * 8 + LV>([&](int tid) { pass_strided<M, +1, false, TC, 1, TCP, NT>(tid, stage, na, TILE, tw); });
+            }
+            ex.template phase<PK_STAGE_ST * 8 + LV>([&](int tid) {
+                for (int i = tid; i < na * M * TC; i += NT) {
+                    const int c = i % TC, r = (i / TC) % M, a = i / (TC * M);
+                    base[(g0 + a) * AS + r * P + c0 + c] = stage[a * TILE + r * TCP + c];
+                }
+            });
+        }
+    }
+}
+
+template <int M, int NT, int STAGE, int TR, bool WRITE_Z, bool LPF, int HOUT, int HP, int LV, class Exec>
+WST_D void ifft_rows_final_staged(Exec& ex, cfloat* base, int narr, int AS, const cfloat* tw, const float* g,
+                                  cfloat* stage) {
+    constexpr int P = M + 1, HALF = M / 2, TILE = 2 * TR * P;
+    constexpr int NAB = STAGE / TILE;
+    static_assert(NAB >= 1 && HALF % TR == 0, "stage too small for a row-pair tile");
+    for (int g0 = 0; g0 < narr; g0 += NAB) {
+        const int na = narr - g0 < NAB ? narr - g0 : NAB;
+        for (int x0 = 0; x0 < HALF; x0 += TR) {
+            // tile row q < TR holds array row x0 + q, tile row TR + q holds array row x0 + q + M/2
+            ex.template phase<PK_STAGE_LD * 8 + LV>([&](int tid) {
+                for (int i = tid; i < na * 2 * TR * M; i += NT) {
+                    const int c = i % M, q = (i / M) % (2 * TR), a = i / (M * 2 * TR);
+                    const int row = x0 + (q < TR ? q : q - TR + HALF);
+                    stage_copy(stage + a * TILE + q * P + c, base + (g0 + a) * AS + row * P + c);
+                }
+                stage_copy_wait();
+            });
+            if constexpr (Fft1<M>::R1 > 1) {
+                ex.template phase<PK_IFFT_ROW_C * 8 + LV>([&](int tid) { pass_contig<M, +1, true, 2 * TR, P, 1, NT>(tid, stage, na, TILE, tw); });
+            }
+            ex.template phase<PK_IFFT_FINAL * 8 + LV>([&](int tid) {
+                pass_rows_final<M, NT, WRITE_Z, LPF, HOUT, HP, false, TR, TR * P>(tid, stage, na, TILE, g);
+            });
+            ex.template phase<PK_STAGE_ST * 8 + LV>([&](int tid) {
+                for (int i = tid; i < na * 2 * TR * M; i += NT) {
+                    const int c = i % M, q = (i / M) % (2 * TR), a = i / (M * 2 * TR);
+                    const int row = x0 + (q < TR ? q : q - TR + HALF);
+                    base[(g0 + a) * AS + row * P + c] = stage[a * TILE + q * P + c];
+                }
+            });
+        }
+    }
+}
+
 // Inverse 2-D FFT of narr digit-swapped M x M spectra (pitch M+1) + modulus (+ row-paired z for a following
 // rfft2_from_pairs) + low-pass map of every array.
-template <int M, int NT, int LV, bool WRITE_Z, int HOUT, int HP, int LPSLOTS, bool GLOB = false, class Exec, class CoefFn>
+template <int M, int NT, int LV, bool WRITE_Z, int HOUT, int HP, int LPSLOTS, bool GLOB = false, int STAGE = 0, int TR = 1,
+          class Exec, class CoefFn>
 WST_D void ifft2_modulus_lowpass(Exec& ex, cfloat* base, int narr, const cfloat* tw, const float* g,
-                                 const float (&w)[kLpTaps], float* lpbuf, float* maps, CoefFn coef) {
+                                 const float (&w)[kLpTaps], float* lpbuf, float* maps, cfloat* stage, CoefFn coef) {
     constexpr int P = M + 1, AS = M * (M + 1);
     constexpr bool FUSED = (Fft1<M>::R1 == 1) ? !WRITE_Z
                                               : (WRITE_Z ? (HOUT <= Fft1<M>::R1) : (HOUT / 2 <= Fft1<M>::R1));
+    if constexpr (GLOB && STAGE > 0) {
+        ifft_cols_staged<M, NT, STAGE, LV>(ex, base, narr, AS, tw, stage);
+        ifft_rows_final_staged<M, NT, STAGE, TR, FUSED ? WRITE_Z : true, FUSED, HOUT, HP, LV>(ex, base, narr, AS, tw, g, stage);
+        if constexpr (FUSED) lowpass_reduce<M, NT, WRITE_Z, HOUT, HP, LPSLOTS, LV>(ex, base, narr, AS, g, lpbuf, maps, coef);
+        else lowpass_maps<M, HOUT, HP, NT, LV, false>(ex, base, AS, narr, g, g, w, maps, coef);
+        return;
+    }
     fft_lines_inv<M, M, 1, P, NT, PK_IFFT_COL_C * 8 + LV, PK_IFFT_COL_S * 8 + LV>(ex, base, narr, AS, tw);   // columns
     if constexpr (Fft1<M>::R1 > 1) {
         ex.template phase<PK_IFFT_ROW_C * 8 + LV>([&](int tid) { pass_contig<M, +1, true, M, P, 1, NT, GLOB>(tid, base, narr, AS, tw); });
@@ -950,6 +1055,7 @@ struct Cascade {
     cfloat* twsm;        // shared twiddles   (C::tw_total)
     float* gsm;          // shared low-pass operators (C::g_total)
     float* lpbuf;        // shared scratch of the fused low-pass reduction (C::lpbuf_floats())
+    cfloat* stage;       // shared tile of the staged passes (C::stage_cfloats(); global-workspace variant only)
     cfloat* u0h;         // per-CTA global scratch: N * (N/2+1)
     float* maps;         // this signal's output maps [K][HOUT][HOUT]
 
@@ -1011,8 +1117,8 @@ struct Cascade {
                 product_fold<MP, MC, G, NT>(tid, uh_parent, pt.psi2[J2][J1] + (size_t)grp * MP * MP * G,
                                             pt.bb2[pair_index(J2, J1)][grp][0], pt.bb2[pair_index(J2, J1)][grp][1], sm);
             });
-            ifft2_modulus_lowpass<MC, NT, J2, false, HOUT, HP, C::LP_SLOTS, C::WS_GLOBAL>(
-                ex, sm, G, tw(J2), g(J2), pt.lpw[J2], lpbuf, maps,
+            ifft2_modulus_lowpass<MC, NT, J2, false, HOUT, HP, C::LP_SLOTS, C::WS_GLOBAL, C::stage_cfloats(), C::stage_rows(MC)>(
+                ex, sm, G, tw(J2), g(J2), pt.lpw[J2], lpbuf, maps, stage,
                 [&](int a) { int t2 = grp * G + a; return t2 < L ? cbase + t2 : -1; });
         }
     }
@@ -1027,8 +1133,8 @@ struct Cascade {
                 product_fold<N, M, GPn, NT>(tid, u0h, pt.psi1[J1] + (size_t)grp * N * N * GPn,
                                             pt.bb1[J1][grp][0], pt.bb1[J1][grp][1], sm);
             });
-            ifft2_modulus_lowpass<M, NT, J1, C::has_children(J1), HOUT, HP, C::LP_SLOTS, C::WS_GLOBAL>(
-                ex, sm, GPn, tw(J1), g(J1), pt.lpw[J1], lpbuf, maps,
+            ifft2_modulus_lowpass<M, NT, J1, C::has_children(J1), HOUT, HP, C::LP_SLOTS, C::WS_GLOBAL, C::stage_cfloats(), C::stage_rows(M)>(
+                ex, sm, GPn, tw(J1), g(J1), pt.lpw[J1], lpbuf, maps, stage,
                 [&](int a) { int t1 = grp * GPn + a; return t1 < L ? 1 + J1 * L + t1 : -1; });
             if constexpr (C::has_children(J1)) {
                 if (pt.max_order >= 2) {
