@@ -552,11 +552,99 @@ WST_D void lowpass_reduce(Exec& ex, cfloat* base, int narr, int AS, const float*
     });
 }
 
+// Tile loads of the staged passes: asynchronous 8-byte global -> shared copies (LDGSTS), so that a thread's whole
+// share of the tile is in flight at once instead of one register round trip after another; stage_copy_wait() closes the
+// phase that issued them.  (Host emulation: plain copies.)
+WST_D void stage_copy(cfloat* dst_shared, const cfloat* src_global) {
+#ifdef __CUDA_ARCH__
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_shared);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src_global) : "memory");
+#else
+    *dst_shared = *src_global;
+#endif
+}
+WST_D void stage_copy_wait() {
+#ifdef __CUDA_ARCH__
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+
+// Global-workspace variant of rfft2_from_pairs: the two row passes and the split run on shared-memory tiles of TZ rows
+// of z (read once, coalesced; the split writes whole rows of U^), the two column passes on tiles of 16 columns of U^.
+template <int M, int NT, int STAGE, int LV, class Exec>
+WST_D void rfft2_from_pairs_staged(Exec& ex, cfloat* z, int ZS, cfloat* uh, int narr, const cfloat* tw, cfloat* stage) {
+    constexpr int P = M + 1, HALF = M / 2, PH = M / 2 + 1, UHS = M * PH;
+    {   // rows
+        constexpr int TZ = (HALF % 16 == 0 && 16 * P <= STAGE) ? 16 : (HALF % 8 == 0 && 8 * P <= STAGE) ? 8
+                           : (HALF % 4 == 0 && 4 * P <= STAGE) ? 4 : (HALF % 2 == 0 && 2 * P <= STAGE) ? 2 : 1;
+        constexpr int TILE = TZ * P, NAB = STAGE / TILE;
+        static_assert(NAB >= 1, "stage too small for a row tile");
+        for (int g0 = 0; g0 < narr; g0 += NAB) {
+            const int na = narr - g0 < NAB ? narr - g0 : NAB;
+            for (int x0 = 0; x0 < HALF; x0 += TZ) {
+                ex.template phase<PK_STAGE_LD * 8 + LV>([&](int tid) {
+                    for (int i = tid; i < na * TZ * M; i += NT) {
+                        const int c = i % M, q = (i / M) % TZ, a = i / (M * TZ);
+                        stage_copy(stage + a * TILE + q * P + c, z + (g0 + a) * ZS + (x0 + q) * P + c);
+                    }
+                    stage_copy_wait();
+                });
+                if constexpr (Fft1<M>::R1 > 1) {
+                    ex.template phase<PK_RFFT_ROW_S * 8 + LV>([&](int tid) { pass_strided<M, -1, true, TZ, P, 1, NT>(tid, stage, na, TILE, tw); });
+                }
+                ex.template phase<PK_RFFT_ROW_C * 8 + LV>([&](int tid) { pass_contig<M, -1, false, TZ, P, 1, NT>(tid, stage, na, TILE, tw); });
+                // split the packed rows:  A = FFT(row x), B = FFT(row x + M/2); consecutive threads write consecutive l
+                ex.template phase<PK_RFFT_SPLIT * 8 + LV>([&](int tid) {
+                    for (int b = tid; b < na * TZ * PH; b += NT) {
+                        const int l = b % PH, q = (b / PH) % TZ, a = b / (PH * TZ);
+                        const cfloat* zr = stage + a * TILE + q * P;
+                        const cfloat zl = zr[Fft1<M>::pi(l)];
+                        const cfloat zm = zr[Fft1<M>::pi(l == 0 ? 0 : M - l)];
+                        cfloat* u = uh + (g0 + a) * UHS + l;
+                        u[(x0 + q) * PH] = cmake(0.5f * (zl.x + zm.x), 0.5f * (zl.y - zm.y));
+                        u[(x0 + q + HALF) * PH] = cmake(0.5f * (zl.y + zm.y), -0.5f * (zl.x - zm.x));
+                    }
+                });
+            }
+        }
+    }
+    {   // columns of U^ (PH of them, not a multiple of the tile width: the last tile is partly idle)
+        constexpr int TC = M * 17 <= STAGE ? 16 : M * 9 <= STAGE ? 8 : M * 5 <= STAGE ? 4 : 2;
+        constexpr int TCP = TC + 1, TILE = M * TCP, NAB = STAGE / TILE;
+        static_assert(NAB >= 1, "stage too small for a column tile");
+        for (int g0 = 0; g0 < narr; g0 += NAB) {
+            const int na = narr - g0 < NAB ? narr - g0 : NAB;
+            for (int c0 = 0; c0 < PH; c0 += TC) {
+                const int tc = PH - c0 < TC ? PH - c0 : TC;
+                ex.template phase<PK_STAGE_LD * 8 + LV>([&](int tid) {
+                    for (int i = tid; i < na * M * TC; i += NT) {
+                        const int c = i % TC, r = (i / TC) % M, a = i / (TC * M);
+                        if (c < tc) stage_copy(stage + a * TILE + r * TCP + c, uh + (g0 + a) * UHS + r * PH + c0 + c);
+                        else stage[a * TILE + r * TCP + c] = cmake(0.f, 0.f);
+                    }
+                    stage_copy_wait();
+                });
+                if constexpr (Fft1<M>::R1 > 1) {
+                    ex.template phase<PK_RFFT_COL_S * 8 + LV>([&](int tid) { pass_strided<M, -1, true, TC, 1, TCP, NT>(tid, stage, na, TILE, tw); });
+                }
+                ex.template phase<PK_RFFT_COL_C * 8 + LV>([&](int tid) { pass_contig<M, -1, false, TC, 1, TCP, NT>(tid, stage, na, TILE, tw); });
+                ex.template phase<PK_STAGE_ST * 8 + LV>([&](int tid) {
+                    for (int i = tid; i < na * M * TC; i += NT) {
+                        const int c = i % TC, r = (i / TC) % M, a = i / (TC * M);
+                        if (c < tc) uh[(g0 + a) * UHS + r * PH + c0 + c] = stage[a * TILE + r * TCP + c];
+                    }
+                });
+            }
+        }
+    }
+}
+
 // Real 2-D forward FFT of narr paired-row arrays z (stride ZS, pitch M+1, M/2 rows) into
 // half spectra U^[pi(k)][l], l = 0..M/2 (stride UHS = M*(M/2+1), pitch M/2+1).
-template <int M, int NT, int LV, bool GLOB = false, class Exec>
-WST_D void rfft2_from_pairs(Exec& ex, cfloat* z, int ZS, cfloat* uh, int narr, const cfloat* tw) {
+template <int M, int NT, int LV, bool GLOB = false, int STAGE = 0, class Exec>
+WST_D void rfft2_from_pairs(Exec& ex, cfloat* z, int ZS, cfloat* uh, int narr, const cfloat* tw, cfloat* stage = nullptr) {
     constexpr int P = M + 1, HALF = M / 2, PH = M / 2 + 1, UHS = M * PH;
+    if constexpr (GLOB && STAGE > 0) { rfft2_from_pairs_staged<M, NT, STAGE, LV>(ex, z, ZS, uh, narr, tw, stage); return; }
     // rows of z (along y): natural -> swapped
     fft_lines_fwd<M, HALF, P, 1, NT, PK_RFFT_ROW_S * 8 + LV, PK_RFFT_ROW_C * 8 + LV, GLOB>(ex, z, narr, ZS, tw);
     // split the packed rows:  A = FFT(row x), B = FFT(row x + M/2)
@@ -930,23 +1018,6 @@ WST_D void lowpass_maps(Exec& ex, cfloat* z, int ZS, int narr, const float* gr, 
     else lowpass_maps_dense<M, HOUT, HP, NT, LV>(ex, z, ZS, narr, gr, gc, maps, coef);
 }
 
-// Tile loads of the staged passes: asynchronous 8-byte global -> shared copies (LDGSTS), so that a thread's whole
-// share of the tile is in flight at once instead of one register round trip after another; stage_copy_wait() closes the
-// phase that issued them.  (Host emulation: plain copies.)
-WST_D void stage_copy(cfloat* dst_shared, const cfloat* src_global) {
-#ifdef __CUDA_ARCH__
-    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_shared);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src_global) : "memory");
-#else
-    *dst_shared = *src_global;
-#endif
-}
-WST_D void stage_copy_wait() {
-#ifdef __CUDA_ARCH__
-    asm volatile("cp.async.wait_all;" ::: "memory");
-#endif
-}
-
 // Global-workspace variant: both passes of the inverse column transforms on shared-memory tiles of TC columns (all M
 // rows; as many arrays per tile batch as the stage holds), then the row pass and the final pass (modulus, pairing,
 // first low-pass contraction) on tiles of TR row pairs.  An array is read and written once per dimension instead of
@@ -1100,7 +1171,7 @@ struct Cascade {
         lowpass_maps<N, HOUT, HP, NT, 0, lp_banded(N, HOUT, 0) && !C::WS_GLOBAL>(ex, sm, 0, 1, g(0), g(0), pt.lpw[0], maps,
                                                                               [](int) { return 0; });
         cfloat* uh = sm + C::OFFB(0);
-        rfft2_from_pairs<N, NT, 0, C::WS_GLOBAL>(ex, sm, 0, uh, 1, tw(0));
+        rfft2_from_pairs<N, NT, 0, C::WS_GLOBAL, C::stage_cfloats()>(ex, sm, 0, uh, 1, tw(0), stage);
         ex.template phase<PK_U0_STORE * 8>([&](int tid) {
             for (int o = tid; o < N * PH; o += NT) u0h[o] = uh[o];
         });
@@ -1139,7 +1210,7 @@ struct Cascade {
             if constexpr (C::has_children(J1)) {
                 if (pt.max_order >= 2) {
                     cfloat* uh = sm + C::OFFB(J1);
-                    rfft2_from_pairs<M, NT, J1, C::WS_GLOBAL>(ex, sm, C::vsz(M), uh, GPn, tw(J1));
+                    rfft2_from_pairs<M, NT, J1, C::WS_GLOBAL, C::stage_cfloats()>(ex, sm, C::vsz(M), uh, GPn, tw(J1), stage);
                     for (int g = 0; g < GPn; ++g) {
                         int t1 = grp * GPn + g;
                         if (t1 >= L) break;
