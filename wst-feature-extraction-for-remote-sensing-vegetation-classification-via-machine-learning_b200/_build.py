@@ -12,7 +12,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 OBJ = os.path.join(PKG_DIR, "_obj")
 LIB_PATH = os.path.join(PKG_DIR, os.environ.get("WST_BUILD_LIB", "libwst_b200.so"))
-NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
+NVCC_FLAGS = os.environ.get("WST_BUILD_DEFS", "").split() + ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC"]
 # The global-workspace variant (CFGG entries: sides whose arrays do not fit in shared memory): threads per CTA (two
 # CTAs share an SM), CTAs per cluster (1: one CTA per signal; the cluster form is kept as a tuning knob, it measured

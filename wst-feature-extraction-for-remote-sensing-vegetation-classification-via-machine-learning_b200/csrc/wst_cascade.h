@@ -135,6 +135,12 @@ WST_CX bool lp_banded(int m, int hout, int level) {
     return r > 0 && s * (hout + 2) == m && (2 * r + 1) * 3 <= m && (level == 0 || s >= 8);
 }
 
+#ifndef WST_STAGE_TC_MAX
+#define WST_STAGE_TC_MAX 16
+#endif
+// columns per staged tile of the global-workspace variant: the largest power of two <= WST_STAGE_TC_MAX dividing m
+WST_CX int stage_tc(int m) { int t = WST_STAGE_TC_MAX; while (m % t) t /= 2; return t; }
+
 // ------------------------------------------------------------------ geometry shared by host and device
 // WS_GLOBAL = false: the data region lives in shared memory (the fast path, N <= 160).
 // WS_GLOBAL = true : same program, data region in a per-CTA global-memory workspace — correct for sides whose
@@ -224,16 +230,18 @@ struct Cfg {
         return false;
     }
     // (array, row-chunk) partial maps held between the two reduce phases: ~10 KB, at least one slot per array
-    static constexpr int LP_SLOTS = cx_max(8, cx_min(40, 2560 / (HOUT * HOUT)));
+    // (the global-workspace variant keeps them in its workspace and takes enough chunks for every thread to have work:
+    // with one chunk per array the reduction of eight 288-row arrays would be 128 work items for 512 threads)
+    static constexpr int LP_SLOTS = WS_GLOBAL_ ? 256 : cx_max(8, cx_min(40, 2560 / (HOUT * HOUT)));
     static WST_CX int lpbuf_floats() { return any_fused() ? LP_SLOTS * HOUT * HOUT : 0; }
     // bytes of dynamic shared memory, and of per-CTA global workspace (0 for the shared-memory variant)
     static WST_CX size_t smem_bytes() {
         return (size_t)((WS_GLOBAL ? 0 : smem_cfloats()) + tw_total + stage_cfloats()) * sizeof(cfloat)
-               + (size_t)(g_total + (CL > 1 ? 0 : lpbuf_floats())) * sizeof(float);
+               + (size_t)(g_total + (WS_GLOBAL ? 0 : lpbuf_floats())) * sizeof(float);
     }
     // Global-workspace variant: the passes of an inverse FFT run on shared-memory tiles (a batch of columns, then a
     // batch of row pairs) so that each array crosses HBM once per dimension instead of once per pass.
-    static WST_CX int stage_cols(int m) { int t = 16; while (m % t) t /= 2; return t; }          // columns per tile
+    static WST_CX int stage_cols(int m) { return stage_tc(m); }                                 // columns per tile
     static WST_CX int stage_cfloats() { return WS_GLOBAL ? N * (stage_cols(N) + 1) : 0; }      // one level-0 column tile
     static WST_CX int stage_rows(int m) {                                                       // row pairs per tile
         int t = 16;
@@ -249,7 +257,7 @@ struct Cfg {
         return m < 1 ? 1 : m;
     }
     static WST_CX size_t workspace_cfloats() {
-        return WS_GLOBAL ? (size_t)smem_cfloats() + (CL > 1 ? (size_t)(lpbuf_floats() + 1) / 2 : 0) : 0;
+        return WS_GLOBAL ? (size_t)smem_cfloats() + (size_t)(lpbuf_floats() + 1) / 2 : 0;
     }
     static_assert(level_total(0, 1) <= BUDGET, "padded size too large for the shared-memory cascade");
 };
@@ -1024,7 +1032,7 @@ WST_D void lowpass_maps(Exec& ex, cfloat* z, int ZS, int narr, const float* gr, 
 // once per pass; tile loads and stores move 8*TC-byte / whole-row segments.
 template <int M, int NT, int STAGE, int LV, class Exec>
 WST_D void ifft_cols_staged(Exec& ex, cfloat* base, int narr, int AS, const cfloat* tw, cfloat* stage) {
-    constexpr int P = M + 1, TC = (M % 16 == 0) ? 16 : (M % 8 == 0) ? 8 : (M % 4 == 0) ? 4 : 2, TCP = TC + 1, TILE = M * TCP;
+    constexpr int P = M + 1, TC = stage_tc(M), TCP = TC + 1, TILE = M * TCP;
     constexpr int NAB = STAGE / TILE;
     static_assert(NAB >= 1, "stage too small for a column tile");
     for (int g0 = 0; g0 < narr; g0 += NAB) {

@@ -31,9 +31,9 @@ __device__ __forceinline__ void run_cascade(Exec& ex, const PlanTables& pt, cons
     cfloat* sm = C::WS_GLOBAL ? workspace + (size_t)slot * C::workspace_cfloats() : sbase;
     cfloat* twsm = C::WS_GLOBAL ? sbase : sbase + C::smem_cfloats();
     float* gsm = reinterpret_cast<float*>(twsm + C::tw_total);
-    float* lpbuf = C::CL > 1 ? reinterpret_cast<float*>(sm + C::smem_cfloats()) : gsm + C::g_total;
+    float* lpbuf = C::WS_GLOBAL ? reinterpret_cast<float*>(sm + C::smem_cfloats()) : gsm + C::g_total;
     // tile of the staged FFT passes (global-workspace variant), after the tables; 8-byte aligned: all counts are even
-    cfloat* stage = reinterpret_cast<cfloat*>(gsm + C::g_total + (C::CL > 1 ? 0 : C::lpbuf_floats()));
+    cfloat* stage = reinterpret_cast<cfloat*>(gsm + C::g_total + (C::WS_GLOBAL ? 0 : C::lpbuf_floats()));
     const size_t map_elems = (size_t)pt.K * C::HOUT * C::HOUT;
     Cascade<C, Exec> prog{ex, pt, sm, twsm, gsm, lpbuf, stage,
                           u0h_scratch + (size_t)slot * (C::N * (C::N / 2 + 1)), nullptr};
