@@ -135,6 +135,9 @@ WST_CX bool lp_banded(int m, int hout, int level) {
     return r > 0 && s * (hout + 2) == m && (2 * r + 1) * 3 <= m && (level == 0 || s >= 8);
 }
 
+#ifndef WST_STAGE_BUFS
+#define WST_STAGE_BUFS 1
+#endif
 #ifndef WST_STAGE_TC_MAX
 #define WST_STAGE_TC_MAX 16
 #endif
@@ -236,13 +239,14 @@ struct Cfg {
     static WST_CX int lpbuf_floats() { return any_fused() ? LP_SLOTS * HOUT * HOUT : 0; }
     // bytes of dynamic shared memory, and of per-CTA global workspace (0 for the shared-memory variant)
     static WST_CX size_t smem_bytes() {
-        return (size_t)((WS_GLOBAL ? 0 : smem_cfloats()) + tw_total + stage_cfloats()) * sizeof(cfloat)
+        return (size_t)((WS_GLOBAL ? 0 : smem_cfloats()) + tw_total + STAGE_BUFS * stage_cfloats()) * sizeof(cfloat)
                + (size_t)(g_total + (WS_GLOBAL ? 0 : lpbuf_floats())) * sizeof(float);
     }
     // Global-workspace variant: the passes of an inverse FFT run on shared-memory tiles (a batch of columns, then a
     // batch of row pairs) so that each array crosses HBM once per dimension instead of once per pass.
     static WST_CX int stage_cols(int m) { return stage_tc(m); }                                 // columns per tile
     static WST_CX int stage_cfloats() { return WS_GLOBAL ? N * (stage_cols(N) + 1) : 0; }      // one level-0 column tile
+    static constexpr int STAGE_BUFS = WST_STAGE_BUFS;   // 2: tile t+1 is loaded (asynchronously) while tile t is transformed
     static WST_CX int stage_rows(int m) {                                                       // row pairs per tile
         int t = 16;
         while (t > 1 && ((m / 2) % t != 0 || 2 * t * (m + 1) > stage_cfloats())) t /= 2;
@@ -577,73 +581,111 @@ WST_D void stage_copy_wait() {
 #endif
 }
 
+// Tile loop of the staged passes.  load(tid, t, buf) issues the asynchronous copies of tile t, first(tid, t, buf) is the
+// first transform pass, mid(t, buf) runs the remaining transform phases, store(tid, t, buf) writes the tile back.
+// With WST_STAGE_BUFS = 2 the loop is software-pipelined: tile t lives in stage buffer t & 1 and the copies of tile
+// t + 1 are issued at the start of tile t's first pass and awaited in its store phase.  Measured slower at 512 x 512 J=5
+// (786 against 914 tiles/s: the second 78 KB buffer has to be paid for with shared memory that the L1 of the product
+// phases was using, and issuing the copies lengthens the transform phases by most of what the load phase took), so the
+// default is one buffer.
+template <int TAG_FIRST, int TAG_ST, int LV, class Exec, class Load, class First, class Mid, class Store>
+WST_D void staged_tiles(Exec& ex, int ntiles, cfloat* stage, int stage_cf, Load load, First first, Mid mid, Store store) {
+    constexpr bool PIPE = WST_STAGE_BUFS > 1;
+    if constexpr (PIPE) ex.template phase<PK_STAGE_LD * 8 + LV>([&](int tid) { load(tid, 0, stage); stage_copy_wait(); });
+    for (int t = 0; t < ntiles; ++t) {
+        cfloat* cur = PIPE ? stage + (t & 1) * stage_cf : stage;
+        cfloat* nxt = stage + ((t + 1) & 1) * stage_cf;
+        if constexpr (!PIPE) ex.template phase<PK_STAGE_LD * 8 + LV>([&](int tid) { load(tid, t, cur); stage_copy_wait(); });
+        ex.template phase<TAG_FIRST * 8 + LV>([&](int tid) {
+            if (PIPE && t + 1 < ntiles) load(tid, t + 1, nxt);
+            first(tid, t, cur);
+        });
+        mid(t, cur);
+        ex.template phase<TAG_ST * 8 + LV>([&](int tid) { store(tid, t, cur); if (PIPE) stage_copy_wait(); });
+    }
+}
+
 // Global-workspace variant of rfft2_from_pairs: the two row passes and the split run on shared-memory tiles of TZ rows
 // of z (read once, coalesced; the split writes whole rows of U^), the two column passes on tiles of 16 columns of U^.
 template <int M, int NT, int STAGE, int LV, class Exec>
 WST_D void rfft2_from_pairs_staged(Exec& ex, cfloat* z, int ZS, cfloat* uh, int narr, const cfloat* tw, cfloat* stage) {
     constexpr int P = M + 1, HALF = M / 2, PH = M / 2 + 1, UHS = M * PH;
+    constexpr bool TWO = Fft1<M>::R1 > 1;
     {   // rows
         constexpr int TZ = (HALF % 16 == 0 && 16 * P <= STAGE) ? 16 : (HALF % 8 == 0 && 8 * P <= STAGE) ? 8
                            : (HALF % 4 == 0 && 4 * P <= STAGE) ? 4 : (HALF % 2 == 0 && 2 * P <= STAGE) ? 2 : 1;
-        constexpr int TILE = TZ * P, NAB = STAGE / TILE;
+        constexpr int TILE = TZ * P, NAB = STAGE / TILE, NX = HALF / TZ;
         static_assert(NAB >= 1, "stage too small for a row tile");
-        for (int g0 = 0; g0 < narr; g0 += NAB) {
-            const int na = narr - g0 < NAB ? narr - g0 : NAB;
-            for (int x0 = 0; x0 < HALF; x0 += TZ) {
-                ex.template phase<PK_STAGE_LD * 8 + LV>([&](int tid) {
-                    for (int i = tid; i < na * TZ * M; i += NT) {
-                        const int c = i % M, q = (i / M) % TZ, a = i / (M * TZ);
-                        stage_copy(stage + a * TILE + q * P + c, z + (g0 + a) * ZS + (x0 + q) * P + c);
-                    }
-                    stage_copy_wait();
-                });
-                if constexpr (Fft1<M>::R1 > 1) {
-                    ex.template phase<PK_RFFT_ROW_S * 8 + LV>([&](int tid) { pass_strided<M, -1, true, TZ, P, 1, NT>(tid, stage, na, TILE, tw); });
+        const int nbatch = (narr + NAB - 1) / NAB;
+        auto geom = [&](int t, int& g0, int& na, int& x0) { g0 = (t / NX) * NAB; na = narr - g0 < NAB ? narr - g0 : NAB; x0 = (t % NX) * TZ; };
+        staged_tiles<TWO ? PK_RFFT_ROW_S : PK_RFFT_ROW_C, PK_RFFT_SPLIT, LV>(ex, nbatch * NX, stage, STAGE,
+            [&](int tid, int t, cfloat* buf) {
+                int g0, na, x0; geom(t, g0, na, x0);
+                for (int i = tid; i < na * TZ * M; i += NT) {
+                    const int c = i % M, q = (i / M) % TZ, a = i / (M * TZ);
+                    stage_copy(buf + a * TILE + q * P + c, z + (g0 + a) * ZS + (x0 + q) * P + c);
                 }
-                ex.template phase<PK_RFFT_ROW_C * 8 + LV>([&](int tid) { pass_contig<M, -1, false, TZ, P, 1, NT>(tid, stage, na, TILE, tw); });
-                // split the packed rows:  A = FFT(row x), B = FFT(row x + M/2); consecutive threads write consecutive l
-                ex.template phase<PK_RFFT_SPLIT * 8 + LV>([&](int tid) {
-                    for (int b = tid; b < na * TZ * PH; b += NT) {
-                        const int l = b % PH, q = (b / PH) % TZ, a = b / (PH * TZ);
-                        const cfloat* zr = stage + a * TILE + q * P;
-                        const cfloat zl = zr[Fft1<M>::pi(l)];
-                        const cfloat zm = zr[Fft1<M>::pi(l == 0 ? 0 : M - l)];
-                        cfloat* u = uh + (g0 + a) * UHS + l;
-                        u[(x0 + q) * PH] = cmake(0.5f * (zl.x + zm.x), 0.5f * (zl.y - zm.y));
-                        u[(x0 + q + HALF) * PH] = cmake(0.5f * (zl.y + zm.y), -0.5f * (zl.x - zm.x));
-                    }
-                });
-            }
-        }
+            },
+            [&](int tid, int t, cfloat* buf) {
+                int g0, na, x0; geom(t, g0, na, x0);
+                if constexpr (TWO) pass_strided<M, -1, true, TZ, P, 1, NT>(tid, buf, na, TILE, tw);
+                else pass_contig<M, -1, false, TZ, P, 1, NT>(tid, buf, na, TILE, tw);
+            },
+            [&](int t, cfloat* buf) {
+                if constexpr (TWO) {
+                    int g0, na, x0; geom(t, g0, na, x0);
+                    ex.template phase<PK_RFFT_ROW_C * 8 + LV>([&](int tid) { pass_contig<M, -1, false, TZ, P, 1, NT>(tid, buf, na, TILE, tw); });
+                }
+            },
+            // split the packed rows:  A = FFT(row x), B = FFT(row x + M/2); consecutive threads write consecutive l
+            [&](int tid, int t, cfloat* buf) {
+                int g0, na, x0; geom(t, g0, na, x0);
+                for (int b = tid; b < na * TZ * PH; b += NT) {
+                    const int l = b % PH, q = (b / PH) % TZ, a = b / (PH * TZ);
+                    const cfloat* zr = buf + a * TILE + q * P;
+                    const cfloat zl = zr[Fft1<M>::pi(l)];
+                    const cfloat zm = zr[Fft1<M>::pi(l == 0 ? 0 : M - l)];
+                    cfloat* u = uh + (g0 + a) * UHS + l;
+                    u[(x0 + q) * PH] = cmake(0.5f * (zl.x + zm.x), 0.5f * (zl.y - zm.y));
+                    u[(x0 + q + HALF) * PH] = cmake(0.5f * (zl.y + zm.y), -0.5f * (zl.x - zm.x));
+                }
+            });
     }
     {   // columns of U^ (PH of them, not a multiple of the tile width: the last tile is partly idle)
         constexpr int TC = M * 17 <= STAGE ? 16 : M * 9 <= STAGE ? 8 : M * 5 <= STAGE ? 4 : 2;
-        constexpr int TCP = TC + 1, TILE = M * TCP, NAB = STAGE / TILE;
+        constexpr int TCP = TC + 1, TILE = M * TCP, NAB = STAGE / TILE, NCT = (PH + TC - 1) / TC;
         static_assert(NAB >= 1, "stage too small for a column tile");
-        for (int g0 = 0; g0 < narr; g0 += NAB) {
-            const int na = narr - g0 < NAB ? narr - g0 : NAB;
-            for (int c0 = 0; c0 < PH; c0 += TC) {
-                const int tc = PH - c0 < TC ? PH - c0 : TC;
-                ex.template phase<PK_STAGE_LD * 8 + LV>([&](int tid) {
-                    for (int i = tid; i < na * M * TC; i += NT) {
-                        const int c = i % TC, r = (i / TC) % M, a = i / (TC * M);
-                        if (c < tc) stage_copy(stage + a * TILE + r * TCP + c, uh + (g0 + a) * UHS + r * PH + c0 + c);
-                        else stage[a * TILE + r * TCP + c] = cmake(0.f, 0.f);
-                    }
-                    stage_copy_wait();
-                });
-                if constexpr (Fft1<M>::R1 > 1) {
-                    ex.template phase<PK_RFFT_COL_S * 8 + LV>([&](int tid) { pass_strided<M, -1, true, TC, 1, TCP, NT>(tid, stage, na, TILE, tw); });
+        const int nbatch = (narr + NAB - 1) / NAB;
+        auto geom = [&](int t, int& g0, int& na, int& c0, int& tc) {
+            g0 = (t / NCT) * NAB; na = narr - g0 < NAB ? narr - g0 : NAB; c0 = (t % NCT) * TC; tc = PH - c0 < TC ? PH - c0 : TC;
+        };
+        staged_tiles<TWO ? PK_RFFT_COL_S : PK_RFFT_COL_C, PK_STAGE_ST, LV>(ex, nbatch * NCT, stage, STAGE,
+            [&](int tid, int t, cfloat* buf) {
+                int g0, na, c0, tc; geom(t, g0, na, c0, tc);
+                for (int i = tid; i < na * M * TC; i += NT) {
+                    const int c = i % TC, r = (i / TC) % M, a = i / (TC * M);
+                    if (c < tc) stage_copy(buf + a * TILE + r * TCP + c, uh + (g0 + a) * UHS + r * PH + c0 + c);
+                    else buf[a * TILE + r * TCP + c] = cmake(0.f, 0.f);
                 }
-                ex.template phase<PK_RFFT_COL_C * 8 + LV>([&](int tid) { pass_contig<M, -1, false, TC, 1, TCP, NT>(tid, stage, na, TILE, tw); });
-                ex.template phase<PK_STAGE_ST * 8 + LV>([&](int tid) {
-                    for (int i = tid; i < na * M * TC; i += NT) {
-                        const int c = i % TC, r = (i / TC) % M, a = i / (TC * M);
-                        if (c < tc) uh[(g0 + a) * UHS + r * PH + c0 + c] = stage[a * TILE + r * TCP + c];
-                    }
-                });
-            }
-        }
+            },
+            [&](int tid, int t, cfloat* buf) {
+                int g0, na, c0, tc; geom(t, g0, na, c0, tc);
+                if constexpr (TWO) pass_strided<M, -1, true, TC, 1, TCP, NT>(tid, buf, na, TILE, tw);
+                else pass_contig<M, -1, false, TC, 1, TCP, NT>(tid, buf, na, TILE, tw);
+            },
+            [&](int t, cfloat* buf) {
+                if constexpr (TWO) {
+                    int g0, na, c0, tc; geom(t, g0, na, c0, tc);
+                    ex.template phase<PK_RFFT_COL_C * 8 + LV>([&](int tid) { pass_contig<M, -1, false, TC, 1, TCP, NT>(tid, buf, na, TILE, tw); });
+                }
+            },
+            [&](int tid, int t, cfloat* buf) {
+                int g0, na, c0, tc; geom(t, g0, na, c0, tc);
+                for (int i = tid; i < na * M * TC; i += NT) {
+                    const int c = i % TC, r = (i / TC) % M, a = i / (TC * M);
+                    if (c < tc) uh[(g0 + a) * UHS + r * PH + c0 + c] = buf[a * TILE + r * TCP + c];
+                }
+            });
     }
 }
 
@@ -1032,66 +1074,80 @@ WST_D void lowpass_maps(Exec& ex, cfloat* z, int ZS, int narr, const float* gr, 
 // once per pass; tile loads and stores move 8*TC-byte / whole-row segments.
 template <int M, int NT, int STAGE, int LV, class Exec>
 WST_D void ifft_cols_staged(Exec& ex, cfloat* base, int narr, int AS, const cfloat* tw, cfloat* stage) {
-    constexpr int P = M + 1, TC = stage_tc(M), TCP = TC + 1, TILE = M * TCP;
+    constexpr int P = M + 1, TC = stage_tc(M), TCP = TC + 1, TILE = M * TCP, NCT = M / TC;
     constexpr int NAB = STAGE / TILE;
+    constexpr bool TWO = Fft1<M>::R1 > 1;
     static_assert(NAB >= 1, "stage too small for a column tile");
-    for (int g0 = 0; g0 < narr; g0 += NAB) {
-        const int na = narr - g0 < NAB ? narr - g0 : NAB;
-        for (int c0 = 0; c0 < M; c0 += TC) {
-            ex.template phase<PK_STAGE_LD * 8 + LV>([&](int tid) {
-                for (int i = tid; i < na * M * TC; i += NT) {
-                    const int c = i % TC, r = (i / TC) % M, a = i / (TC * M);
-                    stage_copy(stage + a * TILE + r * TCP + c, base + (g0 + a) * AS + r * P + c0 + c);
-                }
-                stage_copy_wait();
-            });
-            ex.template phase<PK_IFFT_COL_C * 8 + LV>([&](int tid) { pass_contig<M, +1, true, TC, 1, TCP, NT>(tid, stage, na, TILE, tw); });
-            if constexpr (Fft1<M>::R1 > 1) {
-                ex.template phase<PK_IFFT_COL_S * 8 + LV>([&](int tid) { pass_strided<M, +1, false, TC, 1, TCP, NT>(tid, stage, na, TILE, tw); });
+    const int nbatch = (narr + NAB - 1) / NAB;
+    auto geom = [&](int t, int& g0, int& na, int& c0) { g0 = (t / NCT) * NAB; na = narr - g0 < NAB ? narr - g0 : NAB; c0 = (t % NCT) * TC; };
+    staged_tiles<PK_IFFT_COL_C, PK_STAGE_ST, LV>(ex, nbatch * NCT, stage, STAGE,
+        [&](int tid, int t, cfloat* buf) {
+            int g0, na, c0; geom(t, g0, na, c0);
+            for (int i = tid; i < na * M * TC; i += NT) {
+                const int c = i % TC, r = (i / TC) % M, a = i / (TC * M);
+                stage_copy(buf + a * TILE + r * TCP + c, base + (g0 + a) * AS + r * P + c0 + c);
             }
-            ex.template phase<PK_STAGE_ST * 8 + LV>([&](int tid) {
-                for (int i = tid; i < na * M * TC; i += NT) {
-                    const int c = i % TC, r = (i / TC) % M, a = i / (TC * M);
-                    base[(g0 + a) * AS + r * P + c0 + c] = stage[a * TILE + r * TCP + c];
-                }
-            });
-        }
-    }
+        },
+        [&](int tid, int t, cfloat* buf) {
+            int g0, na, c0; geom(t, g0, na, c0);
+            pass_contig<M, +1, true, TC, 1, TCP, NT>(tid, buf, na, TILE, tw);
+        },
+        [&](int t, cfloat* buf) {
+            if constexpr (TWO) {
+                int g0, na, c0; geom(t, g0, na, c0);
+                ex.template phase<PK_IFFT_COL_S * 8 + LV>([&](int tid) { pass_strided<M, +1, false, TC, 1, TCP, NT>(tid, buf, na, TILE, tw); });
+            }
+        },
+        [&](int tid, int t, cfloat* buf) {
+            int g0, na, c0; geom(t, g0, na, c0);
+            for (int i = tid; i < na * M * TC; i += NT) {
+                const int c = i % TC, r = (i / TC) % M, a = i / (TC * M);
+                base[(g0 + a) * AS + r * P + c0 + c] = buf[a * TILE + r * TCP + c];
+            }
+        });
 }
 
 template <int M, int NT, int STAGE, int TR, bool WRITE_Z, bool LPF, int HOUT, int HP, int LV, class Exec>
 WST_D void ifft_rows_final_staged(Exec& ex, cfloat* base, int narr, int AS, const cfloat* tw, const float* g,
                                   cfloat* stage) {
-    constexpr int P = M + 1, HALF = M / 2, TILE = 2 * TR * P;
+    constexpr int P = M + 1, HALF = M / 2, TILE = 2 * TR * P, NX = HALF / TR;
     constexpr int NAB = STAGE / TILE;
+    constexpr bool TWO = Fft1<M>::R1 > 1;
     static_assert(NAB >= 1 && HALF % TR == 0, "stage too small for a row-pair tile");
-    for (int g0 = 0; g0 < narr; g0 += NAB) {
-        const int na = narr - g0 < NAB ? narr - g0 : NAB;
-        for (int x0 = 0; x0 < HALF; x0 += TR) {
-            // tile row q < TR holds array row x0 + q, tile row TR + q holds array row x0 + q + M/2
-            ex.template phase<PK_STAGE_LD * 8 + LV>([&](int tid) {
-                for (int i = tid; i < na * 2 * TR * M; i += NT) {
-                    const int c = i % M, q = (i / M) % (2 * TR), a = i / (M * 2 * TR);
-                    const int row = x0 + (q < TR ? q : q - TR + HALF);
-                    stage_copy(stage + a * TILE + q * P + c, base + (g0 + a) * AS + row * P + c);
-                }
-                stage_copy_wait();
-            });
-            if constexpr (Fft1<M>::R1 > 1) {
-                ex.template phase<PK_IFFT_ROW_C * 8 + LV>([&](int tid) { pass_contig<M, +1, true, 2 * TR, P, 1, NT>(tid, stage, na, TILE, tw); });
+    const int nbatch = (narr + NAB - 1) / NAB;
+    auto geom = [&](int t, int& g0, int& na, int& x0) { g0 = (t / NX) * NAB; na = narr - g0 < NAB ? narr - g0 : NAB; x0 = (t % NX) * TR; };
+    // tile row q < TR holds array row x0 + q, tile row TR + q holds array row x0 + q + M/2
+    auto final_pass = [&](int tid, int na, cfloat* buf) {
+        pass_rows_final<M, NT, WRITE_Z, LPF, HOUT, HP, false, TR, TR * P>(tid, buf, na, TILE, g);
+    };
+    staged_tiles<TWO ? PK_IFFT_ROW_C : PK_IFFT_FINAL, PK_STAGE_ST, LV>(ex, nbatch * NX, stage, STAGE,
+        [&](int tid, int t, cfloat* buf) {
+            int g0, na, x0; geom(t, g0, na, x0);
+            for (int i = tid; i < na * 2 * TR * M; i += NT) {
+                const int c = i % M, q = (i / M) % (2 * TR), a = i / (M * 2 * TR);
+                const int row = x0 + (q < TR ? q : q - TR + HALF);
+                stage_copy(buf + a * TILE + q * P + c, base + (g0 + a) * AS + row * P + c);
             }
-            ex.template phase<PK_IFFT_FINAL * 8 + LV>([&](int tid) {
-                pass_rows_final<M, NT, WRITE_Z, LPF, HOUT, HP, false, TR, TR * P>(tid, stage, na, TILE, g);
-            });
-            ex.template phase<PK_STAGE_ST * 8 + LV>([&](int tid) {
-                for (int i = tid; i < na * 2 * TR * M; i += NT) {
-                    const int c = i % M, q = (i / M) % (2 * TR), a = i / (M * 2 * TR);
-                    const int row = x0 + (q < TR ? q : q - TR + HALF);
-                    base[(g0 + a) * AS + row * P + c] = stage[a * TILE + q * P + c];
-                }
-            });
-        }
-    }
+        },
+        [&](int tid, int t, cfloat* buf) {
+            int g0, na, x0; geom(t, g0, na, x0);
+            if constexpr (TWO) pass_contig<M, +1, true, 2 * TR, P, 1, NT>(tid, buf, na, TILE, tw);
+            else final_pass(tid, na, buf);
+        },
+        [&](int t, cfloat* buf) {
+            if constexpr (TWO) {
+                int g0, na, x0; geom(t, g0, na, x0);
+                ex.template phase<PK_IFFT_FINAL * 8 + LV>([&](int tid) { final_pass(tid, na, buf); });
+            }
+        },
+        [&](int tid, int t, cfloat* buf) {
+            int g0, na, x0; geom(t, g0, na, x0);
+            for (int i = tid; i < na * 2 * TR * M; i += NT) {
+                const int c = i % M, q = (i / M) % (2 * TR), a = i / (M * 2 * TR);
+                const int row = x0 + (q < TR ? q : q - TR + HALF);
+                base[(g0 + a) * AS + row * P + c] = buf[a * TILE + q * P + c];
+            }
+        });
 }
 
 // Inverse 2-D FFT of narr digit-swapped M x M spectra (pitch M+1) + modulus (+ row-paired z for a following
