@@ -19,7 +19,7 @@ NVCC_FLAGS = os.environ.get("WST_BUILD_DEFS", "").split() + ["-std=c++17", "-O3"
 # slower), and the data-region budget in cfloats that sizes the per-signal working set (Cfg::BUDGET).
 # The environment overrides exist for tuning runs: WST_BUILD_NTL / WST_BUILD_CL / WST_BUILD_BUDGET, and WST_BUILD_LIB
 # names the output library (the same variable selects the library at run time, see tools/tune_variants.sh).
-GLOBAL_VARIANT_THREADS = int(os.environ.get("WST_BUILD_NTL", 512))
+GLOBAL_VARIANT_THREADS = int(os.environ.get("WST_BUILD_NTL", 256))
 GLOBAL_VARIANT_CLUSTER = int(os.environ.get("WST_BUILD_CL", 1))
 GLOBAL_VARIANT_BUDGET = int(os.environ.get("WST_BUILD_BUDGET", 1 << 20))
 

@@ -220,7 +220,9 @@ struct Cfg {
     static constexpr int tw_total = (2 * N - (N >> (J - 1)) + 7) & ~7;   // sum_j N>>j, padded to 8
     // low-pass operator tables G[j][m_j][HP] (floats), one per level, resident in shared memory
     static WST_CX int g_offset(int j) { return tw_offset(j) * HP; }
-    static constexpr int g_total = tw_total * HP;
+    // (the global-workspace variant reads them from global memory through L1 instead: without their 74 KB two CTAs fit
+    // on an SM, and one CTA's tile loads then overlap the other's transforms — 914 -> 971 tiles/s at 512 x 512 J=5)
+    static constexpr int g_total = WS_GLOBAL_ ? 0 : tw_total * HP;
     // The low-pass of an array can be fused into the last pass of its inverse FFT when the 2*HOUT
     // partial sums of a thread fit in the shared-memory slots that thread owns (see pass_rows_final).
     static WST_CX bool lp_fused(int m, bool write_z) {
@@ -1195,7 +1197,7 @@ struct Cascade {
     float* maps;         // this signal's output maps [K][HOUT][HOUT]
 
     WST_D const cfloat* tw(int j) const { return twsm + C::tw_offset(j); }
-    WST_D const float* g(int j) const { return gsm + C::g_offset(j); }
+    WST_D const float* g(int j) const { return C::g_total == 0 ? pt.gr[j] : gsm + C::g_offset(j); }
 
     // index of the first order-2 coefficient of parent (j1, t1)
     WST_D int order2_base(int j1, int t1) const {
@@ -1212,7 +1214,8 @@ struct Cascade {
                 constexpr int m = C::msize(j);
                 const int lt = tid % C::NTL;      // every CTA of a cluster fills its own copy of the tables
                 for (int i = lt; i < m; i += C::NTL) twsm[C::tw_offset(j) + i] = pt.tw[j][i];
-                for (int i = lt; i < m * HP; i += C::NTL) gsm[C::g_offset(j) + i] = pt.gr[j][i];
+                if (C::g_total > 0)
+                    for (int i = lt; i < m * HP; i += C::NTL) gsm[C::g_offset(j) + i] = pt.gr[j][i];
             });
         });
     }
