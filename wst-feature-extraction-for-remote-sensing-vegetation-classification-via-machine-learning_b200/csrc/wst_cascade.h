@@ -474,15 +474,35 @@ WST_D void pass_rows_final(int tid, cfloat* base, int narr, int AS, const float*
         else { x = b % HALF; int r = b / HALF; i2 = r % nsub; g = r / nsub; }
         cfloat* p0 = base + g * AS + x * P + i2;
         cfloat* p1 = p0 + POFF;
-        cfloat a[NV], c[NV];
-        static_for<0, NV>([&](auto K) { constexpr int k = decltype(K)::value; a[k] = p0[k * YS]; c[k] = p1[k * YS]; });
-        dft<NV, +1>(a);
-        dft<NV, +1>(c);
-        static_for<0, NV>([&](auto K) {
-            constexpr int k = decltype(K)::value;
-            a[k].x = cabs_(a[k]);
-            a[k].y = cabs_(c[k]);
-        });
+        cfloat a[NV];
+        if constexpr (NV > 16) {
+            // long butterflies (the 24-point lines of 576): one row at a time, so that only one butterfly's 2*NV
+            // registers are live together with the NV moduli of the other
+            float mc[NV];
+            {
+                cfloat c[NV];
+                static_for<0, NV>([&](auto K) { constexpr int k = decltype(K)::value; c[k] = p1[k * YS]; });
+                dft<NV, +1>(c);
+                static_for<0, NV>([&](auto K) { constexpr int k = decltype(K)::value; mc[k] = cabs_(c[k]); });
+            }
+            static_for<0, NV>([&](auto K) { constexpr int k = decltype(K)::value; a[k] = p0[k * YS]; });
+            dft<NV, +1>(a);
+            static_for<0, NV>([&](auto K) {
+                constexpr int k = decltype(K)::value;
+                a[k].x = cabs_(a[k]);
+                a[k].y = mc[k];
+            });
+        } else {
+            cfloat c[NV];
+            static_for<0, NV>([&](auto K) { constexpr int k = decltype(K)::value; a[k] = p0[k * YS]; c[k] = p1[k * YS]; });
+            dft<NV, +1>(a);
+            dft<NV, +1>(c);
+            static_for<0, NV>([&](auto K) {
+                constexpr int k = decltype(K)::value;
+                a[k].x = cabs_(a[k]);
+                a[k].y = cabs_(c[k]);
+            });
+        }
         if constexpr (LPF) {
             float acc0[HOUT], acc1[HOUT];
             static_for<0, HOUT>([&](auto I) { acc0[decltype(I)::value] = 0.f; acc1[decltype(I)::value] = 0.f; });

@@ -50,7 +50,7 @@ __device__ __forceinline__ void run_cascade(Exec& ex, const PlanTables& pt, cons
 // workspace) runs the whole scattering cascade of one (patch, channel) signal at a time (wst_cascade.h).
 template <class C>
 __global__ void __launch_bounds__(C::NTL, C::min_ctas())
-cascade_kernel(const PlanTables pt, const InputDesc in, long long nsig, cfloat* u0h_scratch,
+cascade_kernel(const __grid_constant__ PlanTables pt, const InputDesc in, long long nsig, cfloat* u0h_scratch,
                cfloat* workspace, float* maps_out, float* maps_scratch, float* feats) {
     DevExec<C::CL> ex{C::CL > 1 ? cluster_cta_rank() * C::NTL : 0};
     run_cascade<C>(ex, pt, in, nsig, u0h_scratch, workspace, maps_out, maps_scratch, feats);
@@ -59,7 +59,7 @@ cascade_kernel(const PlanTables pt, const InputDesc in, long long nsig, cfloat* 
 // Debug twin: same program, executor that accumulates clock64() per phase tag; CTA 0's totals -> cycles.
 template <class C>
 __global__ void __launch_bounds__(C::NTL, 1)
-cascade_prof_kernel(const PlanTables pt, const InputDesc in, long long nsig, cfloat* u0h_scratch,
+cascade_prof_kernel(const __grid_constant__ PlanTables pt, const InputDesc in, long long nsig, cfloat* u0h_scratch,
                     cfloat* workspace, float* maps_out, float* maps_scratch, float* feats, long long* cycles) {
     __shared__ long long acc[kNumPhaseTags];
     for (int i = threadIdx.x; i < kNumPhaseTags; i += C::NTL) acc[i] = 0;
