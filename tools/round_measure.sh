@@ -12,3 +12,6 @@ for c in cfg3 cfg5 repo cfg2; do python tools/phase_profile.py $c > $O/${T}_phas
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $O/${T}_ncu_launches_bench_cfg3.csv python bench.py --no-cpu --steps 3 --warmup 3 > $O/${T}_ncu_launches.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:cascade_kernel -s 3 -c 1 -f -o $O/${T}_prof_cfg3_bench python bench.py --no-cpu --steps 1 --warmup 3 > $O/${T}_ncu_full.log 2>&1
 tail -1 $O/${T}_ncu_full.log
+ncu --set full --clock-control none --import-source on -k regex:cascade_kernel -s 2 -c 1 -f -o $O/${T}_prof_cfg5 python tools/ncu_target.py cfg5 2 > $O/${T}_ncu_full_cfg5.log 2>&1
+tail -1 $O/${T}_ncu_full_cfg5.log
+python tools/aux_bench.py > $O/${T}_aux_bench.json 2>/dev/null
