@@ -148,3 +148,29 @@ def test_noise_feeds_the_uint8_ingest_and_dropins():
                wst_b200.add_poisson_noise, wst_b200.add_uniform_noise):
         out = fn(img, 25)
         assert out.dtype == np.uint8 and out.shape == img.shape and not np.array_equal(out, img)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(1, 2, 2, 2), (3, 5, 7, 3), (2, 33, 17, 4), (0, 8, 8, 3)])
+@pytest.mark.parametrize("kind", ["gaussian", "salt_and_pepper", "speckle", "poisson", "uniform"])
+def test_kernel_ragged_shapes_with_reference_draws(kind, shape):
+    """Odd sizes, more than three channels, the smallest image the reference's salt-and-pepper accepts, an empty batch."""
+    import wst_b200
+    from oracle import add_noise as ora
+    rng = np.random.default_rng(sum(shape))
+    imgs = rng.integers(0, 256, shape, dtype=np.uint8)
+    if shape[0] == 0:
+        out = wst_b200.add_noise(torch.from_numpy(imgs).cuda(), kind, 25, seed=1)
+        assert tuple(out.shape) == shape
+        return
+    np.random.seed(42)
+    d = [ora.draw(kind, im, 25) for im in imgs]
+    ref = np.stack([ora.apply(kind, im, 25, di) for im, di in zip(imgs, d)])
+    if kind == "salt_and_pepper":
+        draws = np.stack([np.stack([s, p]) for s, p in d]).astype(np.int64)
+    else:
+        draws = np.stack(d).astype(np.int64 if kind == "poisson" else np.float64)
+    got = wst_b200.add_noise(torch.from_numpy(imgs).cuda(), kind, 25, draws=torch.from_numpy(np.ascontiguousarray(draws)).cuda())
+    np.testing.assert_array_equal(got.cpu().numpy(), ref)
+    rnd = wst_b200.add_noise(torch.from_numpy(imgs).cuda(), kind, 25, seed=3)          # device generator: shape and range only
+    assert tuple(rnd.shape) == shape and rnd.dtype == torch.uint8
