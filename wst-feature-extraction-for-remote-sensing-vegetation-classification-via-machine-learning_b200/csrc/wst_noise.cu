@@ -61,27 +61,31 @@ struct Philox {
         const double u1 = 1.0 - uniform(), u2 = uniform();
         return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
     }
+    // 24-bit uniform in (0, 1) for the rejection tests below
+    __device__ float uniformf() { return ((float)(next32() >> 8) + 0.5f) * (1.0f / 16777216.0f); }
     // Poisson(lam): sequential search below 10, Hörmann's transformed rejection (PTRS, 1993) from 10 up — the
-    // same two regimes numpy's generator uses.
-    __device__ long long poisson(double lam) {
-        if (lam <= 0.0) return 0;
-        if (lam < 10.0) {
-            const double enlam = exp(-lam);
+    // same two regimes numpy's generator uses.  The draw is an integer decided by accept/reject tests, for which
+    // single precision is ample (and twice as fast as the double-precision logarithms and lgamma).
+    __device__ long long poisson(double lam_d) {
+        if (lam_d <= 0.0) return 0;
+        const float lam = (float)lam_d;
+        if (lam < 10.0f) {
+            const float enlam = __expf(-lam);
             long long k = 0;
-            double prod = uniform();
-            while (prod > enlam) { ++k; prod *= uniform(); }
+            float prod = uniformf();
+            while (prod > enlam) { ++k; prod *= uniformf(); }
             return k;
         }
-        const double slam = sqrt(lam), loglam = log(lam);
-        const double b = 0.931 + 2.53 * slam, a = -0.059 + 0.02483 * b;
-        const double invalpha = 1.1239 + 1.1328 / (b - 3.4), vr = 0.9277 - 3.6224 / (b - 2.0);
+        const float slam = sqrtf(lam), loglam = __logf(lam);
+        const float b = 0.931f + 2.53f * slam, a = -0.059f + 0.02483f * b;
+        const float invalpha = 1.1239f + 1.1328f / (b - 3.4f), vr = 0.9277f - 3.6224f / (b - 2.0f);
         for (;;) {
-            const double U = uniform() - 0.5, V = uniform();
-            const double us = 0.5 - fabs(U);
-            const double kf = floor((2.0 * a / us + b) * U + lam + 0.43);
-            if (us >= 0.07 && V <= vr) return (long long)kf;
-            if (kf < 0.0 || (us < 0.013 && V > us)) continue;
-            if (log(V) + log(invalpha) - log(a / (us * us) + b) <= -lam + kf * loglam - lgamma(kf + 1.0))
+            const float U = uniformf() - 0.5f, V = uniformf();
+            const float us = 0.5f - fabsf(U);
+            const float kf = floorf((2.0f * a / us + b) * U + lam + 0.43f);
+            if (us >= 0.07f && V <= vr) return (long long)kf;
+            if (kf < 0.0f || (us < 0.013f && V > us)) continue;
+            if (__logf(V) + __logf(invalpha) - __logf(a / (us * us) + b) <= -lam + kf * loglam - lgammaf(kf + 1.0f))
                 return (long long)kf;
         }
     }
