@@ -643,9 +643,11 @@ WST_D void rfft2_from_pairs_staged(Exec& ex, cfloat* z, int ZS, cfloat* uh, int 
         staged_tiles<TWO ? PK_RFFT_ROW_S : PK_RFFT_ROW_C, PK_RFFT_SPLIT, LV>(ex, nbatch * NX, stage, STAGE,
             [&](int tid, int t, cfloat* buf) {
                 int g0, na, x0; geom(t, g0, na, x0);
-                for (int i = tid; i < na * TZ * M; i += NT) {
-                    const int c = i % M, q = (i / M) % TZ, a = i / (M * TZ);
-                    stage_copy(buf + a * TILE + q * P + c, z + (g0 + a) * ZS + (x0 + q) * P + c);
+                for (int rq = tid >> 5; rq < na * TZ; rq += NT / 32) {       // one warp per tile row, lanes along it
+                    const int q = rq % TZ, a = rq / TZ;
+                    const cfloat* src = z + (g0 + a) * ZS + (x0 + q) * P;
+                    cfloat* dst = buf + a * TILE + q * P;
+                    for (int c = tid & 31; c < M; c += 32) stage_copy(dst + c, src + c);
                 }
             },
             [&](int tid, int t, cfloat* buf) {
@@ -662,14 +664,17 @@ WST_D void rfft2_from_pairs_staged(Exec& ex, cfloat* z, int ZS, cfloat* uh, int 
             // split the packed rows:  A = FFT(row x), B = FFT(row x + M/2); consecutive threads write consecutive l
             [&](int tid, int t, cfloat* buf) {
                 int g0, na, x0; geom(t, g0, na, x0);
-                for (int b = tid; b < na * TZ * PH; b += NT) {
-                    const int l = b % PH, q = (b / PH) % TZ, a = b / (PH * TZ);
+                for (int rq = tid >> 5; rq < na * TZ; rq += NT / 32) {
+                    const int q = rq % TZ, a = rq / TZ;
                     const cfloat* zr = buf + a * TILE + q * P;
-                    const cfloat zl = zr[Fft1<M>::pi(l)];
-                    const cfloat zm = zr[Fft1<M>::pi(l == 0 ? 0 : M - l)];
-                    cfloat* u = uh + (g0 + a) * UHS + l;
-                    u[(x0 + q) * PH] = cmake(0.5f * (zl.x + zm.x), 0.5f * (zl.y - zm.y));
-                    u[(x0 + q + HALF) * PH] = cmake(0.5f * (zl.y + zm.y), -0.5f * (zl.x - zm.x));
+                    cfloat* ua = uh + (g0 + a) * UHS + (x0 + q) * PH;
+                    cfloat* ub = ua + HALF * PH;
+                    for (int l = tid & 31; l < PH; l += 32) {
+                        const cfloat zl = zr[Fft1<M>::pi(l)];
+                        const cfloat zm = zr[Fft1<M>::pi(l == 0 ? 0 : M - l)];
+                        ua[l] = cmake(0.5f * (zl.x + zm.x), 0.5f * (zl.y - zm.y));
+                        ub[l] = cmake(0.5f * (zl.y + zm.y), -0.5f * (zl.x - zm.x));
+                    }
                 }
             });
     }
@@ -684,10 +689,14 @@ WST_D void rfft2_from_pairs_staged(Exec& ex, cfloat* z, int ZS, cfloat* uh, int 
         staged_tiles<TWO ? PK_RFFT_COL_S : PK_RFFT_COL_C, PK_STAGE_ST, LV>(ex, nbatch * NCT, stage, STAGE,
             [&](int tid, int t, cfloat* buf) {
                 int g0, na, c0, tc; geom(t, g0, na, c0, tc);
-                for (int i = tid; i < na * M * TC; i += NT) {
-                    const int c = i % TC, r = (i / TC) % M, a = i / (TC * M);
-                    if (c < tc) stage_copy(buf + a * TILE + r * TCP + c, uh + (g0 + a) * UHS + r * PH + c0 + c);
-                    else buf[a * TILE + r * TCP + c] = cmake(0.f, 0.f);
+                const int c = tid % TC;                                         // TC consecutive threads per tile row
+                for (int a = 0; a < na; ++a) {
+                    const cfloat* src = uh + (g0 + a) * UHS + c0 + c;
+                    cfloat* dst = buf + a * TILE + c;
+                    for (int r = tid / TC; r < M; r += NT / TC) {
+                        if (c < tc) stage_copy(dst + r * TCP, src + r * PH);
+                        else dst[r * TCP] = cmake(0.f, 0.f);
+                    }
                 }
             },
             [&](int tid, int t, cfloat* buf) {
@@ -703,10 +712,13 @@ WST_D void rfft2_from_pairs_staged(Exec& ex, cfloat* z, int ZS, cfloat* uh, int 
             },
             [&](int tid, int t, cfloat* buf) {
                 int g0, na, c0, tc; geom(t, g0, na, c0, tc);
-                for (int i = tid; i < na * M * TC; i += NT) {
-                    const int c = i % TC, r = (i / TC) % M, a = i / (TC * M);
-                    if (c < tc) uh[(g0 + a) * UHS + r * PH + c0 + c] = buf[a * TILE + r * TCP + c];
-                }
+                const int c = tid % TC;
+                if (c < tc)
+                    for (int a = 0; a < na; ++a) {
+                        cfloat* dst = uh + (g0 + a) * UHS + c0 + c;
+                        const cfloat* src = buf + a * TILE + c;
+                        for (int r = tid / TC; r < M; r += NT / TC) dst[r * PH] = src[r * TCP];
+                    }
             });
     }
 }
@@ -1105,9 +1117,11 @@ WST_D void ifft_cols_staged(Exec& ex, cfloat* base, int narr, int AS, const cflo
     staged_tiles<PK_IFFT_COL_C, PK_STAGE_ST, LV>(ex, nbatch * NCT, stage, STAGE,
         [&](int tid, int t, cfloat* buf) {
             int g0, na, c0; geom(t, g0, na, c0);
-            for (int i = tid; i < na * M * TC; i += NT) {
-                const int c = i % TC, r = (i / TC) % M, a = i / (TC * M);
-                stage_copy(buf + a * TILE + r * TCP + c, base + (g0 + a) * AS + r * P + c0 + c);
+            const int c = tid % TC;                                             // TC consecutive threads per tile row
+            for (int a = 0; a < na; ++a) {
+                const cfloat* src = base + (g0 + a) * AS + c0 + c;
+                cfloat* dst = buf + a * TILE + c;
+                for (int r = tid / TC; r < M; r += NT / TC) stage_copy(dst + r * TCP, src + r * P);
             }
         },
         [&](int tid, int t, cfloat* buf) {
@@ -1122,9 +1136,11 @@ WST_D void ifft_cols_staged(Exec& ex, cfloat* base, int narr, int AS, const cflo
         },
         [&](int tid, int t, cfloat* buf) {
             int g0, na, c0; geom(t, g0, na, c0);
-            for (int i = tid; i < na * M * TC; i += NT) {
-                const int c = i % TC, r = (i / TC) % M, a = i / (TC * M);
-                base[(g0 + a) * AS + r * P + c0 + c] = buf[a * TILE + r * TCP + c];
+            const int c = tid % TC;
+            for (int a = 0; a < na; ++a) {
+                cfloat* dst = base + (g0 + a) * AS + c0 + c;
+                const cfloat* src = buf + a * TILE + c;
+                for (int r = tid / TC; r < M; r += NT / TC) dst[r * P] = src[r * TCP];
             }
         });
 }
@@ -1145,10 +1161,12 @@ WST_D void ifft_rows_final_staged(Exec& ex, cfloat* base, int narr, int AS, cons
     staged_tiles<TWO ? PK_IFFT_ROW_C : PK_IFFT_FINAL, PK_STAGE_ST, LV>(ex, nbatch * NX, stage, STAGE,
         [&](int tid, int t, cfloat* buf) {
             int g0, na, x0; geom(t, g0, na, x0);
-            for (int i = tid; i < na * 2 * TR * M; i += NT) {
-                const int c = i % M, q = (i / M) % (2 * TR), a = i / (M * 2 * TR);
+            for (int rq = tid >> 5; rq < na * 2 * TR; rq += NT / 32) {          // one warp per tile row, lanes along it
+                const int q = rq % (2 * TR), a = rq / (2 * TR);
                 const int row = x0 + (q < TR ? q : q - TR + HALF);
-                stage_copy(buf + a * TILE + q * P + c, base + (g0 + a) * AS + row * P + c);
+                const cfloat* src = base + (g0 + a) * AS + row * P;
+                cfloat* dst = buf + a * TILE + q * P;
+                for (int c = tid & 31; c < M; c += 32) stage_copy(dst + c, src + c);
             }
         },
         [&](int tid, int t, cfloat* buf) {
@@ -1164,10 +1182,12 @@ WST_D void ifft_rows_final_staged(Exec& ex, cfloat* base, int narr, int AS, cons
         },
         [&](int tid, int t, cfloat* buf) {
             int g0, na, x0; geom(t, g0, na, x0);
-            for (int i = tid; i < na * 2 * TR * M; i += NT) {
-                const int c = i % M, q = (i / M) % (2 * TR), a = i / (M * 2 * TR);
+            for (int rq = tid >> 5; rq < na * 2 * TR; rq += NT / 32) {
+                const int q = rq % (2 * TR), a = rq / (2 * TR);
                 const int row = x0 + (q < TR ? q : q - TR + HALF);
-                base[(g0 + a) * AS + row * P + c] = buf[a * TILE + q * P + c];
+                cfloat* dst = base + (g0 + a) * AS + row * P;
+                const cfloat* src = buf + a * TILE + q * P;
+                for (int c = tid & 31; c < M; c += 32) dst[c] = src[c];
             }
         });
 }
