@@ -232,8 +232,10 @@ def to_block(feats_block):
 
 # ----------------------------------------------------------------------------- batched device op (B4)
 def scattering_features(x, J, L=8, max_order=2, layout="block"):
-    """x: [B, C, H, W] float32 CUDA tensor -> [B, C*2*K] pooled features on the same device."""
-    plan = get_plan(x.shape[-2], x.shape[-1], J, L, max_order, x.device)
+    """x: [B, C, H, W] float32 (or [B, H, W, C] uint8, load_rgb_image's input) CUDA tensor -> [B, C*2*K] pooled
+    features on the same device."""
+    H, W = (x.shape[1], x.shape[2]) if x.dtype == torch.uint8 else (x.shape[-2], x.shape[-1])
+    plan = get_plan(H, W, J, L, max_order, x.device)
     feats, _ = plan.forward(x, want_features=True)
     return to_block(feats) if layout == "block" else to_interleaved(feats).contiguous()
 
@@ -409,7 +411,8 @@ def extract_hybrid_features(rgb_image, J=2, L=8):
 
 
 def hybrid_features(x, J, L=8, max_order=2):
-    """Batched device form: x [B, C, H, W] float32 CUDA -> [B, C*18 + C*2*K] (advanced stats block, then WST block)."""
+    """Batched device form: x [B, C, H, W] float32 (or [B, H, W, C] uint8) CUDA -> [B, C*18 + C*2*K] (advanced stats
+    block, then WST block)."""
     adv = advanced_stats(x).reshape(x.shape[0], -1)
     return torch.cat([adv, scattering_features(x, J, L, max_order)], dim=1)
 
