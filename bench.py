@@ -35,6 +35,8 @@ CONFIGS = {   # name -> (M, J, L, max_order, C, default per-GPU batch)
     "cfg3": (128, 4, 8, 2, 3, 4096),
     "repo": (128, 2, 8, 2, 3, 4096),
     "cfg5": (512, 5, 8, 2, 4, 148),
+    "p256j2": (256, 2, 8, 2, 3, 592),
+    "p256j4": (256, 4, 8, 2, 3, 592),
 }
 WORKLOAD_NAMES = {
     "cfg1": "Scattering2D J=2 L=8 max_order=2, 32x32 RGB patches (BASELINE configs[0])",
@@ -42,6 +44,8 @@ WORKLOAD_NAMES = {
     "cfg3": "Scattering2D J=4 L=8 max_order=2, 128x128 RGB patches, batch sharded across GPUs (BASELINE configs[2])",
     "repo": "Scattering2D J=2 L=8 max_order=2, 128x128 RGB patches (the reference's own setting)",
     "cfg5": "Scattering2D J=5 L=8 max_order=2, 512x512 4-band tiles (BASELINE configs[4]; global-workspace cascade)",
+    "p256j2": "Scattering2D J=2 L=8 max_order=2, 256x256 RGB patches (not a BASELINE shape; global-workspace cascade)",
+    "p256j4": "Scattering2D J=4 L=8 max_order=2, 256x256 RGB patches (not a BASELINE shape; global-workspace cascade)",
 }
 
 
