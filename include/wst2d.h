@@ -36,7 +36,7 @@ typedef struct wst2d_plan wst2d_plan;
 
 #define WST2D_OK            0
 #define WST2D_ERR_ARG      (-1)   /* bad argument (NULL, non-positive size, 2^J > min(H,W), ...) */
-#define WST2D_ERR_UNSUPPORTED (-2) /* no compiled cascade for this (padded size, J) */
+#define WST2D_ERR_UNSUPPORTED (-2) /* configuration outside what the library supports (see wst2d_plan_create_ex) */
 #define WST2D_ERR_CUDA     (-3)   /* CUDA runtime error, or no device */
 
 /* Build the filter bank and tables for `Scattering2D(J, shape=(H, W), L, max_order)` on `device`.
@@ -45,6 +45,20 @@ typedef struct wst2d_plan wst2d_plan;
  * output maps (H_p / 2^J - 2) x (W_p / 2^J - 2). */
 int wst2d_plan_create(wst2d_plan** out, int device, int H, int W, int J, int L, int max_order);
 int wst2d_plan_destroy(wst2d_plan* plan);
+
+/* Same with an explicit engine.  The reference builds its transform from whatever image it loads
+ * (train_and_save_model.py:355-359), so every (H, W) with 2^J <= min(H, W), rectangular included, and every L is
+ * accepted:
+ *   WST2D_ENGINE_AUTO        the fused shared-memory FFT cascade when one is compiled for the padded size (square
+ *                            sides 36..160, 264..288, 576 with L <= 8), otherwise WST2D_ENGINE_GEMM_SIMT
+ *   WST2D_ENGINE_FFT         the fused cascade or WST2D_ERR_UNSUPPORTED
+ *   WST2D_ENGINE_GEMM_SIMT   every DFT of the cascade as a dense DFT-matrix product on the fp32 pipe (any size)
+ *   WST2D_ENGINE_GEMM_TF32X3 the same products on the tensor cores as 3xTF32 (fp32-level accuracy)
+ * The environment variable WST_ENGINE=fft|gemm|gemm_tf32x3 overrides AUTO (A/B measurements). */
+enum { WST2D_ENGINE_AUTO = 0, WST2D_ENGINE_FFT = 1, WST2D_ENGINE_GEMM_SIMT = 2, WST2D_ENGINE_GEMM_TF32X3 = 3 };
+int wst2d_plan_create_ex(wst2d_plan** out, int device, int H, int W, int J, int L, int max_order, int engine);
+/* The engine a plan runs on (WST2D_ENGINE_FFT / _GEMM_SIMT / _GEMM_TF32X3). */
+int wst2d_plan_engine(const wst2d_plan* plan);
 
 /* Geometry of a plan; any output pointer may be NULL. */
 int wst2d_query(const wst2d_plan* plan, int* K, int* h, int* w, int* Hp, int* Wp);
@@ -119,9 +133,9 @@ int wst2d_forward_host(const wst2d_plan* plan, const float* x_host, int64_t B, i
  * psi_hat [J*L][Hp][Wp], phi_hat [Hp][Wp]; either may be NULL. */
 int wst2d_plan_filters(const wst2d_plan* plan, float* psi_hat, float* phi_hat);
 
-/* Number of kernels wst2d_forward launches for a batch of B*C signals (for launch accounting): the cascade
- * kernel pools in-kernel, so this is 1 (wst2d_forward_u8 adds its conversion kernel, wst2d_forward_host
- * launches one per chunk). */
+/* Number of kernels wst2d_forward launches for a batch of B*C signals (for launch accounting): the fused cascade
+ * pools in-kernel, so this is 1 (wst2d_forward_host launches one per chunk); the GEMM engines launch one kernel per
+ * matrix product of the cascade and chunk of signals. */
 int wst2d_launch_count(const wst2d_plan* plan, int64_t B, int C);
 
 /* Optional per-kernel timing for bench.py's roofline: when enabled, wst2d_forward records CUDA events
@@ -131,10 +145,11 @@ int wst2d_profile(wst2d_plan* plan, int enable);
 int wst2d_profile_read(wst2d_plan* plan, double* cascade_ms, double* pool_ms, int* cascade_launches);
 
 /* Debug: run the cascade over nsig signals with a cycle-counting executor and return, per phase tag
- * (csrc/wst_cascade.h PhaseKind * 8 + level; ntags must equal the library's tag count, 128), the SM
- * cycles CTA 0 spent in that phase.  Synchronous.  Used by tools/phase_profile.py. */
+ * (csrc/wst_cascade.h PhaseKind * 8 + level; ntags must equal wst2d_debug_num_phase_tags()), the SM
+ * cycles CTA 0 spent in that phase.  Synchronous; fused cascades only.  Used by tools/phase_profile.py. */
 int wst2d_debug_phase_cycles(const wst2d_plan* plan, const float* x_dev, int64_t nsig, int64_t* cycles_host,
                              int ntags);
+int wst2d_debug_num_phase_tags(void);
 
 /* Measured fp32 FMA rate of `device` in TFLOP/s (dependent-chain-free FMA loop on all SMs): the
  * denominator of the compute roofline, which MEASURED_PEAKS.json does not carry. */

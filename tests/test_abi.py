@@ -40,10 +40,14 @@ def test_argument_validation(built_lib):
     assert built_lib.wst2d_plan_create(ctypes.byref(h), 0, 32, 32, 2, 8, 3) == -1          # max_order
     assert built_lib.wst2d_plan_create(ctypes.byref(h), 0, 16, 16, 5, 8, 2) == -1          # 2^J > M
     assert b"2^J" in built_lib.wst2d_last_error()
-    assert built_lib.wst2d_plan_create(ctypes.byref(h), 0, 100, 100, 2, 8, 2) == -2        # no compiled cascade
+    FFT = 1                                                                                # WST2D_ENGINE_FFT
+    assert built_lib.wst2d_plan_create_ex(ctypes.byref(h), 0, 100, 100, 2, 8, 2, FFT) == -2   # no compiled cascade
     assert b"no compiled cascade" in built_lib.wst2d_last_error()
-    assert built_lib.wst2d_plan_create(ctypes.byref(h), 0, 32, 64, 2, 8, 2) == -2          # non-square
-    assert built_lib.wst2d_plan_create(ctypes.byref(h), 0, 32, 32, 2, 16, 2) == -2         # L > 8
+    assert built_lib.wst2d_plan_create_ex(ctypes.byref(h), 0, 32, 64, 2, 8, 2, FFT) == -2     # non-square
+    assert built_lib.wst2d_plan_create_ex(ctypes.byref(h), 0, 32, 32, 2, 16, 2, FFT) == -2    # L > 8
+    assert built_lib.wst2d_plan_create_ex(ctypes.byref(h), 0, 32, 32, 2, 8, 2, 7) == -1       # unknown engine
+    assert built_lib.wst2d_plan_create(ctypes.byref(h), 0, 16, 40, 4, 8, 2) == -2             # pad as wide as the image
+    assert built_lib.wst2d_debug_num_phase_tags() == 168
     assert built_lib.wst2d_query(None, None, None, None, None, None) == -1
     assert built_lib.wst2d_forward(None, None, 1, 1, None, None, None) == -1
     assert built_lib.wst2d_plan_destroy(None) == 0

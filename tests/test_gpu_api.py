@@ -1,0 +1,116 @@
+"""Drop-in surfaces added for the training dispatcher and the inference driver (8b B4), on the GPU
+against the oracle's statement-for-statement wrappers of the reference call sites."""
+import numpy as np
+import pytest
+import torch
+
+from tests.parity import assert_parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def wst():
+    assert torch.cuda.is_available()
+    import wst_b200
+    return wst_b200
+
+
+@pytest.fixture(scope="module")
+def img():
+    rng = np.random.default_rng(21)
+    return (rng.integers(0, 256, (3, 128, 128)) / 255.0).astype(np.float32)
+
+
+def ref_basic(rgb):
+    f = np.zeros(6)                                   # inference.py:170-179
+    for i in range(3):
+        f[2 * i] = np.mean(rgb[i]); f[2 * i + 1] = np.std(rgb[i])
+    return f
+
+
+def test_training_dispatcher(wst, img):
+    """extract_features(img, method), train_and_save_model.py:389-398."""
+    from oracle import extract_wst_features_training
+    from oracle.advanced_stats import extract_advanced_features
+    adv = wst.extract_features(img, "advanced_stats")
+    w = wst.extract_features(img, "wst")
+    hyb = wst.extract_features(img, "hybrid")
+    assert adv.shape == (54,) and adv.dtype == np.float64
+    assert w.shape == (486,) and w.dtype == np.float32
+    assert hyb.shape == (540,) and hyb.dtype == np.float64
+    assert np.array_equal(hyb[:54], adv) and np.array_equal(hyb[54:], w.astype(np.float64))
+    ref = extract_wst_features_training(img, precision="double", cache_filters=True).reshape(3, 2, 81)
+    assert_parity(w.reshape(3, 2, 81)[:, 0], ref[:, 0], 2, 8, what="wst mean")
+    assert_parity(w.reshape(3, 2, 81)[:, 1], ref[:, 1], 2, 8, what="wst std")
+    ra = extract_advanced_features(img)
+    ed = np.arange(54) % 18 == 17                                       # edge density: a fraction of H*W pixels
+    assert np.abs(adv[~ed] - ra[~ed]).max() <= 2e-5 * np.maximum(np.abs(ra[~ed]), 1.0).max()
+    assert np.abs(adv[ed] - ra[ed]).max() <= 1.5 / (128 * 128)
+    assert len(wst.get_feature_names("hybrid")) == hyb.size
+
+
+def test_inference_arms(wst, img):
+    """ModelInference.extract_features, inference.py:272-287: wst -> basic(6) + interleaved WST = 492,
+    hybrid -> advanced(54) + interleaved WST = 540, float64."""
+    from oracle import extract_wst_features_inference
+    ref_w = extract_wst_features_inference(img, cache_filters=True)
+    m = wst.ModelInferenceFeatures()
+    m.feature_method = "wst"
+    f = m.extract_features(img)
+    assert f.shape == (492,) and f.dtype == np.float64
+    assert np.abs(f[:6] - ref_basic(img)).max() <= 2e-6
+    got = f[6:].reshape(3, 81, 2)
+    assert_parity(got[:, :, 0], ref_w.reshape(3, 81, 2)[:, :, 0], 2, 8, what="interleaved mean")
+    assert_parity(got[:, :, 1], ref_w.reshape(3, 81, 2)[:, :, 1], 2, 8, what="interleaved std")
+    m.feature_method = "hybrid"
+    g = m.extract_features(img)
+    assert g.shape == (540,) and np.array_equal(g[54:], f[6:]) and np.array_equal(g[:54], m.extract_advanced_features(img))
+    m.feature_method = "advanced_stats"
+    assert np.array_equal(m.extract_features(img), g[:54])
+    assert np.array_equal(m.extract_wst_features(img, J=2, L=8), f[6:])
+    assert np.array_equal(m.extract_basic_features(img), f[:6])
+    # the block and interleaved layouts hold the same numbers
+    blk = wst.extract_wst_features(img).reshape(3, 2, 81)
+    assert np.array_equal(np.ascontiguousarray(blk.swapaxes(1, 2)).reshape(-1).astype(np.float64), f[6:])
+
+
+def test_non_finite_and_short_inputs_are_refused(wst):
+    bad = np.zeros((3, 32, 32), np.float32); bad[1, 3, 4] = np.nan
+    with pytest.raises(ValueError, match="non-finite"):
+        wst.extract_advanced_features(bad)
+    with pytest.raises(IndexError):
+        wst.extract_advanced_features(np.zeros((2, 32, 32), np.float32))
+    four = np.random.default_rng(0).random((4, 32, 32)).astype(np.float32)
+    assert wst.extract_advanced_features(four).shape == (54,)           # first three channels, like the reference
+
+
+def test_forward_host_validates_out(wst):
+    plan = wst.get_plan(32, 32, 2)
+    x = np.zeros((2, 3, 32, 32), np.float32)
+    for bad in (np.empty((2, 3, 2, 81), np.float64), np.empty((2, 3, 2, 80), np.float32),
+                np.empty((2, 3, 2, 162), np.float32)[..., ::2], torch.empty((2, 3, 2, 81), device="cuda")):
+        with pytest.raises(RuntimeError, match="out"):
+            plan.forward_host(x, out=bad)
+    out = np.empty((2, 3, 2, 81), np.float32)
+    assert plan.forward_host(x, out=out) is out
+    with pytest.raises(RuntimeError, match="cuda:0"):
+        plan.forward(torch.zeros((1, 32, 32, 3), dtype=torch.uint8))     # uint8 path checks the device too
+
+
+def test_torch_library_op(wst):
+    rng = np.random.default_rng(2)
+    x = torch.from_numpy((rng.integers(0, 256, (3, 3, 64, 64)) / 255.0).astype(np.float32)).cuda()
+    plan = wst.get_plan(64, 64, 3)
+    feats, maps = plan.forward(x, True, True)
+    a = torch.ops.wst.scattering2d_features(x, 3, 8, 2, 0, False)
+    assert torch.equal(a, feats.reshape(3, -1))
+    b = torch.ops.wst.scattering2d_features(x, 3, 8, 2, 1, False)
+    assert torch.equal(b, wst.to_interleaved(feats))
+    assert torch.equal(torch.ops.wst.scattering2d_features(x, 3, 8, 2, 0, True), maps)
+    assert torch.equal(torch.ops.wst.scattering2d_maps(x, 3, 8, 2), maps)
+    torch.library.opcheck(torch.ops.wst.scattering2d_features.default, (x, 3, 8, 2, 0, False),
+                          test_utils=("test_schema", "test_faketensor"))
+    compiled = torch.compile(lambda t: torch.ops.wst.scattering2d_features(t, 3, 8, 2, 0, False) * 2.0, fullgraph=True,
+                             backend="aot_eager")          # Dynamo traces through the op (fake kernel), no graph break
+    assert torch.allclose(compiled(x), a * 2.0)

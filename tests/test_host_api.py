@@ -93,3 +93,63 @@ def test_gloo_gather_world2(tmp_path, B):
     full = torch.arange(B * F, dtype=torch.float32).reshape(B, F)
     for r in range(world):
         assert torch.equal(torch.load(os.path.join(tmp_path, "r%d.pt" % r)), full)
+
+
+def test_feature_names_match_reference_contract():
+    """train_and_save_model.py:400-427: the names the trainer zips with the feature columns."""
+    adv = wst_b200.get_feature_names("advanced_stats")
+    wst = wst_b200.get_feature_names("wst")
+    hyb = wst_b200.get_feature_names("hybrid")
+    assert len(adv) == 54 and adv[0] == "R_mean" and adv[17] == "R_edge_density" and adv[18] == "G_mean"
+    assert len(wst) == 486 and wst[0] == "R_wst_mean_0" and wst[81] == "R_wst_std_0" and wst[162] == "G_wst_mean_0"
+    assert hyb == adv + wst and len(hyb) == 540
+    assert len(wst_b200.get_feature_names("wst", K=217)) == 3 * 2 * 217
+    with pytest.raises(ValueError, match="Unknown feature method: foo"):
+        wst_b200.get_feature_names("foo")
+    ref_path = "/root/reference/src/training/train_and_save_model.py"
+    if os.path.exists(ref_path):                       # build container only: the reference's own function
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("ref_train", ref_path)
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+        for m in ("advanced_stats", "wst", "hybrid"):
+            assert wst_b200.get_feature_names(m) == ref.get_feature_names(m)
+
+
+def test_dispatchers_reject_unknown_methods_before_touching_the_gpu():
+    img = np.zeros((3, 32, 32), np.float32)
+    with pytest.raises(ValueError, match="Unknown feature method: nope"):
+        wst_b200.extract_features(img, "nope")
+    with pytest.raises(ValueError, match="Unknown feature method: nope"):
+        wst_b200.extract_features_inference(img, "nope")
+    m = wst_b200.ModelInferenceFeatures()
+    m.feature_method = "nope"
+    with pytest.raises(ValueError, match="Unknown feature method"):
+        m.extract_features(img)
+
+
+def test_torch_library_ops_are_registered_with_fake_kernels():
+    """the batched ops are visible to the dispatcher; shapes propagate without a device."""
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    assert str(torch.ops.wst.scattering2d_features.default._schema).startswith(
+        "wst::scattering2d_features(Tensor x, SymInt J, SymInt L, SymInt max_order, SymInt layout, bool full_maps)")
+    with FakeTensorMode():
+        x = torch.empty((5, 3, 128, 128), device="cuda")
+        assert torch.ops.wst.scattering2d_features(x, 2, 8, 2, 0, False).shape == (5, 486)
+        assert torch.ops.wst.scattering2d_features(x, 4, 8, 2, 1, True).shape == (5, 3, 417, 8, 8)
+        assert torch.ops.wst.scattering2d_maps(x, 2, 8, 2).shape == (5, 3, 81, 32, 32)
+        r = torch.empty((2, 1, 120, 128), device="cuda")                       # rectangular: 32 x 32 outputs at J=2
+        assert torch.ops.wst.scattering2d_maps(r, 2, 8, 2).shape == (2, 1, 81, 30, 32)
+        u = torch.empty((7, 64, 64, 3), device="cuda", dtype=torch.uint8)      # load_rgb_image's input order
+        assert torch.ops.wst.scattering2d_features(u, 3, 8, 2, 0, False).shape == (7, 1302)
+    with pytest.raises(NotImplementedError):                                    # no CPU kernel: no CPU fallback
+        torch.ops.wst.scattering2d_features(torch.zeros(1, 3, 32, 32), 2, 8, 2, 0, False)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        wst_b200.scattering_features(torch.zeros(1, 3, 32, 32), 2)
+
+
+def test_device_index_resolution():
+    from wst_b200._api import _device_index
+    assert _device_index(3) == 3 and _device_index("cuda:2") == 2 and _device_index(torch.device("cuda", 1)) == 1
+    with pytest.raises(RuntimeError, match="CUDA devices only"):
+        _device_index("cpu")

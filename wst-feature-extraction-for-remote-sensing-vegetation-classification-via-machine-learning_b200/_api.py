@@ -25,8 +25,10 @@ __all__ = [
     "Scattering2D", "ScatteringNumPy2D", "ScatteringTorch2D",
     "extract_wst_features", "extract_wst_features_interleaved", "extract_wst_features_gray",
     "compute_scattering_coefficients", "extract_wst_features_batch", "num_coefficients",
-    "compute_padding", "to_interleaved", "to_block", "advanced_stats", "extract_advanced_features",
+    "ENGINES", "compute_padding", "to_interleaved", "to_block", "advanced_stats", "extract_advanced_features",
     "extract_hybrid_features", "hybrid_features", "ADVANCED_STAT_NAMES",
+    "extract_features", "get_feature_names", "extract_basic_features", "basic_stats",
+    "extract_features_inference", "ModelInferenceFeatures",
     "NOISE_TYPES", "add_noise", "add_gaussian_noise", "add_salt_and_pepper_noise", "add_speckle_noise",
     "add_poisson_noise", "add_uniform_noise", "shard_range", "shard_sizes", "gather_features", "fma_peak_tflops",
 ]
@@ -46,19 +48,40 @@ def num_coefficients(J, L=8, max_order=2):
 
 
 # ----------------------------------------------------------------------------- plan
-class Plan:
-    """Owns a wst2d_plan (filter bank + tables on one device) for Scattering2D(J, shape, L, max_order)."""
+def _device_index(device):
+    """CUDA device ordinal of `device` (None or an index-less 'cuda' = the current device)."""
+    if device is None:
+        return torch.cuda.current_device()
+    if isinstance(device, int):
+        return device
+    d = torch.device(device)
+    if d.type != "cuda":
+        raise RuntimeError("wst_b200 runs on CUDA devices only (got %s); there is no CPU fallback." % d)
+    return torch.cuda.current_device() if d.index is None else d.index
 
-    def __init__(self, H, W, J, L=8, max_order=2, device=None):
+
+ENGINES = {"auto": 0, "fft": 1, "gemm": 2, "gemm_tf32x3": 3}      # include/wst2d.h WST2D_ENGINE_*
+
+
+class Plan:
+    """Owns a wst2d_plan (filter bank + tables on one device) for Scattering2D(J, shape, L, max_order).
+
+    engine: "auto" (the fused FFT cascade when one is compiled for the padded size, else the DFT-matrix engine, which
+    takes any H x W and any L), "fft", "gemm" (fp32 SIMT) or "gemm_tf32x3" (tensor cores)."""
+
+    def __init__(self, H, W, J, L=8, max_order=2, device=None, engine="auto"):
         if not torch.cuda.is_available():
             raise RuntimeError("wst_b200: no CUDA device available (this package has no CPU fallback).")
         lib = _lib.load()
-        self.device = torch.cuda.current_device() if device is None else torch.device(device).index or 0
+        self.device = _device_index(device)
         self.H, self.W, self.J, self.L, self.max_order = int(H), int(W), int(J), int(L), int(max_order)
         h = ctypes.c_void_p()
-        _lib.check(lib.wst2d_plan_create(ctypes.byref(h), self.device, self.H, self.W, self.J, self.L,
-                                         self.max_order))
+        if engine not in ENGINES:
+            raise ValueError("engine must be one of %s" % sorted(ENGINES))
+        _lib.check(lib.wst2d_plan_create_ex(ctypes.byref(h), self.device, self.H, self.W, self.J, self.L,
+                                            self.max_order, ENGINES[engine]))
         self._h = h
+        self.engine = {v: k for k, v in ENGINES.items()}[lib.wst2d_plan_engine(h)]
         q = [ctypes.c_int() for _ in range(5)]
         _lib.check(lib.wst2d_query(h, *[ctypes.byref(v) for v in q]))
         self.K, self.h, self.w, self.Hp, self.Wp = [v.value for v in q]
@@ -94,6 +117,8 @@ class Plan:
                 raise RuntimeError("uint8 input must be [B, H, W, C] of spatial size (%i,%i)." % (self.H, self.W))
             if not x.is_cuda or not x.is_contiguous():
                 raise RuntimeError("uint8 input must be a contiguous CUDA tensor.")
+            if x.device.index != self.device:
+                raise RuntimeError("Input tensor must live on cuda:%d." % self.device)
             B, C = x.shape[0], x.shape[3]
         else:
             self._check_x(x)
@@ -145,17 +170,28 @@ class Plan:
         -> feats [B, C, 2, K] numpy float32.  Copies are chunked and overlapped inside the library."""
         lib = _lib.load()
         if isinstance(x, torch.Tensor):
+            if x.is_cuda:
+                raise RuntimeError("forward_host expects host memory; use Plan.forward for CUDA tensors.")
             xa = x.numpy()
         else:
             xa = x
-        if xa.dtype != np.float32 or not xa.flags["C_CONTIGUOUS"] or xa.ndim != 4:
+        if not isinstance(xa, np.ndarray) or xa.dtype != np.float32 or not xa.flags["C_CONTIGUOUS"] or xa.ndim != 4:
             raise RuntimeError("forward_host expects a C-contiguous float32 [B, C, H, W] array.")
         if xa.shape[-2] != self.H or xa.shape[-1] != self.W:
             raise RuntimeError("NumPy array must be of spatial size (%i,%i)." % (self.H, self.W))
         B, C = xa.shape[0], xa.shape[1]
         if out is None:
             out = np.empty((B, C, 2, self.K), np.float32)
-        oa = out.numpy() if isinstance(out, torch.Tensor) else out
+        if isinstance(out, torch.Tensor):
+            if out.is_cuda:
+                raise RuntimeError("forward_host: `out` must be a host (CPU) tensor, not a CUDA tensor.")
+            oa = out.numpy()
+        else:
+            oa = out
+        if not (isinstance(oa, np.ndarray) and oa.dtype == np.float32 and oa.flags["C_CONTIGUOUS"]
+                and oa.flags["WRITEABLE"] and tuple(oa.shape) == (B, C, 2, self.K)):
+            raise RuntimeError("forward_host: `out` must be a writeable C-contiguous float32 array of shape "
+                               "(%d, %d, 2, %d)." % (B, C, self.K))
         _lib.check(lib.wst2d_forward_host(self._h, xa.ctypes.data, B, C, oa.ctypes.data))
         return out
 
@@ -175,7 +211,8 @@ class Plan:
         kinds = ["twiddle", "input", "lp1", "lp2", "rfft_row_s", "rfft_row_c", "rfft_split", "rfft_col_s",
                  "rfft_col_c", "u0_store", "prod1", "prod2", "ifft_col_c", "ifft_col_s", "ifft_row_c", "ifft_final",
                  "lp_reduce", "lp_store", "pool", "stage_load", "stage_store"]
-        n = 8 * len(kinds)
+        n = _lib.load().wst2d_debug_num_phase_tags()
+        assert n == 8 * len(kinds), "phase tag table out of date"
         arr = (ctypes.c_int64 * n)()
         _lib.check(_lib.load().wst2d_debug_phase_cycles(self._h, x.data_ptr(), x.shape[0] * x.shape[1], arr, n))
         return {(kinds[i // 8], i % 8): int(arr[i]) for i in range(n) if arr[i]}
@@ -194,17 +231,17 @@ _PLAN_CACHE = {}
 _PLAN_LOCK = threading.Lock()
 
 
-def get_plan(H, W, J, L=8, max_order=2, device=None):
-    """Plan cache keyed (device, H, W, J, L, max_order): the filter bank is built once, not per image
+def get_plan(H, W, J, L=8, max_order=2, device=None, engine="auto"):
+    """Plan cache keyed (device, H, W, J, L, max_order, engine): the filter bank is built once, not per image
     (the reference rebuilds it per image, train_and_save_model.py:359 — SURVEY.md F5)."""
     if not torch.cuda.is_available():
         raise RuntimeError("wst_b200: no CUDA device available (this package has no CPU fallback).")
-    dev = torch.cuda.current_device() if device is None else (torch.device(device).index or 0)
-    key = (dev, int(H), int(W), int(J), int(L), int(max_order))
+    dev = _device_index(device)
+    key = (dev, int(H), int(W), int(J), int(L), int(max_order), engine)
     with _PLAN_LOCK:
         p = _PLAN_CACHE.get(key)
         if p is None:
-            p = Plan(H, W, J, L, max_order, dev)
+            p = Plan(H, W, J, L, max_order, dev, engine)
             _PLAN_CACHE[key] = p
         return p
 
@@ -233,18 +270,26 @@ def to_block(feats_block):
 # ----------------------------------------------------------------------------- batched device op (B4)
 def scattering_features(x, J, L=8, max_order=2, layout="block"):
     """x: [B, C, H, W] float32 (or [B, H, W, C] uint8, load_rgb_image's input) CUDA tensor -> [B, C*2*K] pooled
-    features on the same device."""
-    H, W = (x.shape[1], x.shape[2]) if x.dtype == torch.uint8 else (x.shape[-2], x.shape[-1])
-    plan = get_plan(H, W, J, L, max_order, x.device)
-    feats, _ = plan.forward(x, want_features=True)
-    return to_block(feats) if layout == "block" else to_interleaved(feats).contiguous()
+    features on the same device.  Dispatches through the registered op torch.ops.wst.scattering2d_features."""
+    if layout not in ("block", "interleaved"):
+        raise ValueError("layout must be 'block' or 'interleaved'")
+    _check_device_op_input(x)
+    from . import _ops  # noqa: F401  (registers the wst:: ops)
+    return torch.ops.wst.scattering2d_features(x, int(J), int(L), int(max_order), 0 if layout == "block" else 1, False)
 
 
 def scattering_maps(x, J, L=8, max_order=2):
-    """x: [B, C, H, W] float32 CUDA tensor -> coefficient maps [B, C, K, h, w]."""
-    plan = get_plan(x.shape[-2], x.shape[-1], J, L, max_order, x.device)
-    _, maps = plan.forward(x, want_features=False, want_maps=True)
-    return maps
+    """x: [B, C, H, W] float32 CUDA tensor -> coefficient maps [B, C, K, h, w] (torch.ops.wst.scattering2d_maps)."""
+    _check_device_op_input(x)
+    from . import _ops  # noqa: F401
+    return torch.ops.wst.scattering2d_maps(x, int(J), int(L), int(max_order))
+
+
+def _check_device_op_input(x):
+    if not isinstance(x, torch.Tensor):
+        raise TypeError("The input should be a PyTorch Tensor.")
+    if not x.is_cuda:
+        raise RuntimeError("wst_b200: the batched ops take CUDA tensors (this package has no CPU fallback).")
 
 
 def scene_features(raster, tile, J, L=8, max_order=2, stride=None, rank=0, world_size=1, gather=False):
@@ -286,7 +331,7 @@ class _ScatteringBase2D:
         self._plan = None
 
     def _get_plan(self, device=None):
-        if self._plan is None or (device is not None and self._plan.device != (torch.device(device).index or 0)):
+        if self._plan is None or (device is not None and self._plan.device != _device_index(device)):
             self._plan = get_plan(self.shape[0], self.shape[1], self.J, self.L, self.max_order, device)
         return self._plan
 
@@ -397,17 +442,111 @@ def advanced_stats(x):
     return out
 
 
-def extract_advanced_features(rgb_image):
-    """Drop-in for train_and_save_model.py:58-112 / inference.py:181-235: [C, H, W] float32 -> float64 [C*18]."""
+def _rgb_to_device(rgb_image, channels=None):
+    """Host [C, H, W] image -> float32 CUDA tensor [1, C', H, W]; rejects non-finite pixels.
+
+    The reference drops non-finite pixels before the moments and percentiles (train_and_save_model.py:66-67) and
+    lets them poison the Sobel / Laplace statistics; its inputs are uint8 PNGs / 255 (load_rgb_image, :51-56) and
+    therefore always finite.  The device kernels assume finite input, so anything else is refused here instead of
+    returning statistics the reference would not produce."""
     if not torch.cuda.is_available():
         raise RuntimeError("wst_b200: no CUDA device available (this package has no CPU fallback).")
-    x = torch.from_numpy(np.ascontiguousarray(np.asarray(rgb_image)[None], dtype=np.float32)).cuda()
-    return advanced_stats(x)[0].reshape(-1).cpu().numpy().astype(np.float64)
+    a = np.asarray(rgb_image)
+    if a.ndim != 3:
+        raise ValueError("rgb_image must be [C, H, W]")
+    if channels is not None:
+        if a.shape[0] < channels:
+            raise IndexError("index %d is out of bounds for axis 0 with size %d" % (a.shape[0], a.shape[0]))
+        a = a[:channels]
+    a = np.ascontiguousarray(a[None], dtype=np.float32)
+    if not np.isfinite(a).all():
+        raise ValueError("wst_b200: non-finite pixels are not supported (the reference's inputs are uint8 / 255).")
+    return torch.from_numpy(a).cuda()
+
+
+def extract_advanced_features(rgb_image):
+    """Drop-in for train_and_save_model.py:58-112 / inference.py:181-235: [C, H, W] float32 -> float64 [3*18].
+    Like the reference, the first three channels are used whatever C is (C < 3 raises IndexError there too)."""
+    return advanced_stats(_rgb_to_device(rgb_image, 3))[0].reshape(-1).cpu().numpy().astype(np.float64)
+
+
+def basic_stats(x):
+    """x: [B, C, H, W] float32 or [B, H, W, C] uint8 CUDA tensor -> [B, C, 2] (mean, population std) per channel:
+    the batched device form of ModelInference.extract_basic_features (inference.py:170-179).  The two numbers are
+    the first two of the advanced-statistics kernel's outputs (double-precision moments)."""
+    return advanced_stats(x)[..., :2].contiguous()
+
+
+def extract_basic_features(rgb_image):
+    """Drop-in for ModelInference.extract_basic_features (inference.py:170-179): [C, H, W] float32 ->
+    float64 [6] = (mean, std) of each of the first three channels."""
+    return basic_stats(_rgb_to_device(rgb_image, 3))[0].reshape(-1).cpu().numpy().astype(np.float64)
 
 
 def extract_hybrid_features(rgb_image, J=2, L=8):
-    """Drop-in for train_and_save_model.py:380-387: concat([advanced stats (C*18), WST (C*2*K)]) -> float64."""
+    """Drop-in for train_and_save_model.py:380-387: concat([advanced stats (3*18), WST (C*2*K)]) -> float64."""
     return np.concatenate([extract_advanced_features(rgb_image), extract_wst_features(rgb_image, J=J, L=L)])
+
+
+def extract_features(rgb_image, feature_method):
+    """Drop-in for the training dispatcher, train_and_save_model.py:389-398."""
+    if feature_method == "advanced_stats":
+        return extract_advanced_features(rgb_image)
+    elif feature_method == "wst":
+        return extract_wst_features(rgb_image)
+    elif feature_method == "hybrid":
+        return extract_hybrid_features(rgb_image)
+    else:
+        raise ValueError(f"Unknown feature method: {feature_method}")
+
+
+def get_feature_names(feature_method, K=81):
+    """Drop-in for train_and_save_model.py:400-427: the column names the Random-Forest trainer zips with the
+    feature matrix.  K = 81 is the reference's hard-coded coefficient count (J=2, L=8); other plans pass their K."""
+    if feature_method == "advanced_stats":
+        return [f"{c}_{stat}" for c in ["R", "G", "B"] for stat in ADVANCED_STAT_NAMES]
+    elif feature_method == "wst":
+        return [f"{channel}_wst_{stat}_{i}" for channel in ["R", "G", "B"] for stat in ["mean", "std"]
+                for i in range(K)]
+    elif feature_method == "hybrid":
+        return get_feature_names("advanced_stats") + get_feature_names("wst", K)
+    else:
+        raise ValueError(f"Unknown feature method: {feature_method}")
+
+
+def extract_features_inference(rgb_image, feature_method, J=2, L=8):
+    """Drop-in for ModelInference.extract_features (inference.py:272-287): 'advanced_stats' -> 54,
+    'wst' -> hstack([basic(6), interleaved WST]) = 492, 'hybrid' -> hstack([advanced(54), interleaved WST]) = 540
+    (float64, the inference driver's column order — SURVEY.md F4)."""
+    if feature_method == "advanced_stats":
+        return extract_advanced_features(rgb_image)
+    elif feature_method == "wst":
+        return np.hstack([extract_basic_features(rgb_image), extract_wst_features_interleaved(rgb_image, J=J, L=L)])
+    elif feature_method == "hybrid":
+        return np.hstack([extract_advanced_features(rgb_image), extract_wst_features_interleaved(rgb_image, J=J, L=L)])
+    else:
+        raise ValueError(f"Unknown feature method: {feature_method}")
+
+
+class ModelInferenceFeatures:
+    """The feature-extraction methods of the reference's ModelInference (inference.py:170-287) backed by the CUDA
+    library, same names and signatures, so that `class ModelInference(ModelInferenceFeatures)` (or assigning the
+    methods) switches the inference driver over without touching predict_single_image (:289-320).
+    `self.feature_method` is what parse_model_directory (:61-124) sets."""
+
+    feature_method = "wst"
+
+    def extract_basic_features(self, rgb_image):
+        return extract_basic_features(rgb_image)
+
+    def extract_advanced_features(self, rgb_image):
+        return extract_advanced_features(rgb_image)
+
+    def extract_wst_features(self, rgb_image, J=2, L=8):
+        return extract_wst_features_interleaved(rgb_image, J=J, L=L)
+
+    def extract_features(self, rgb_image):
+        return extract_features_inference(rgb_image, self.feature_method)
 
 
 def hybrid_features(x, J, L=8, max_order=2):

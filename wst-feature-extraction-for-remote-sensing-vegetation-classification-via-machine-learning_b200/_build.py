@@ -78,7 +78,7 @@ def build_library(force=False, verbose=False):
     o = os.path.join(OBJ, "wst_lib.o")
     objs.append(o)
     jobs.append(([nvcc] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, "wst_lib.cu"), "-o", o], verbose))
-    for unit in ("wst_advstats", "wst_noise"):
+    for unit in ("wst_advstats", "wst_noise", "wst_generic"):
         o = os.path.join(OBJ, unit + ".o")
         objs.append(o)
         jobs.append(([nvcc] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, unit + ".cu"), "-o", o], verbose))

@@ -21,6 +21,7 @@
 #include "wst_tables.h"
 #include "wst_filters.h"
 #include "wst_ops.h"
+#include "wst_generic.h"
 #include "../../include/wst2d.h"
 
 using namespace wst;
@@ -41,41 +42,42 @@ int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
 // ------------------------------------------------------------------------------------------------
 // filter bank (fp64, once per plan)
 // ------------------------------------------------------------------------------------------------
-__global__ void gabor_spatial_kernel(const GaborParams* __restrict__ gp, int nf, int N, double2* out) {
+// M x N grid (x: row index < M, y: column index < N), like kymatio's gabor_2d(M, N, ...)
+__global__ void gabor_spatial_kernel(const GaborParams* __restrict__ gp, int nf, int M, int N, double2* out) {
     int y = blockIdx.x * blockDim.x + threadIdx.x;
     int x = blockIdx.y, f = blockIdx.z;
     if (y >= N || f >= nf) return;
     GaborParams p = gp[f];
     double re, im;
-    gabor_point(p, x, y, N, N, re, im);
-    out[((size_t)f * N + x) * N + y] = make_double2(re, im);
+    gabor_point(p, x, y, M, N, re, im);
+    out[((size_t)f * M + x) * N + y] = make_double2(re, im);
 }
 
-// out[f][k][y] = sum_x W[(k*x) % N] * in[f][x][y],   W[t] = exp(-2 pi i t / N)
+// out[f][k][y] = sum_x W[(k*x) % M] * in[f][x][y],   W[t] = exp(-2 pi i t / M)      (arrays are M x N)
 __global__ void dft_axis0_kernel(const double2* __restrict__ in, double2* __restrict__ out,
-                                 const double2* __restrict__ W, int N) {
+                                 const double2* __restrict__ W, int M, int N) {
     int y = blockIdx.x * blockDim.x + threadIdx.x;
     int k = blockIdx.y, f = blockIdx.z;
     if (y >= N) return;
-    const double2* p = in + (size_t)f * N * N + y;
+    const double2* p = in + (size_t)f * M * N + y;
     double ar = 0.0, ai = 0.0;
     int t = 0;
-    for (int x = 0; x < N; ++x) {
+    for (int x = 0; x < M; ++x) {
         double2 w = W[t], v = p[(size_t)x * N];
         ar += w.x * v.x - w.y * v.y;
         ai += w.x * v.y + w.y * v.x;
-        t += k; if (t >= N) t -= N;
+        t += k; if (t >= M) t -= M;
     }
-    out[((size_t)f * N + k) * N + y] = make_double2(ar, ai);
+    out[((size_t)f * M + k) * N + y] = make_double2(ar, ai);
 }
 
 // out[f][k][l] = sum_y in[f][k][y] * W[(l*y) % N]
 __global__ void dft_axis1_kernel(const double2* __restrict__ in, double2* __restrict__ out,
-                                 const double2* __restrict__ W, int N) {
+                                 const double2* __restrict__ W, int M, int N) {
     int l = blockIdx.x * blockDim.x + threadIdx.x;
     int k = blockIdx.y, f = blockIdx.z;
     if (l >= N) return;
-    const double2* p = in + ((size_t)f * N + k) * N;
+    const double2* p = in + ((size_t)f * M + k) * N;
     double ar = 0.0, ai = 0.0;
     int t = 0;
     for (int y = 0; y < N; ++y) {
@@ -84,13 +86,12 @@ __global__ void dft_axis1_kernel(const double2* __restrict__ in, double2* __rest
         ai += w.x * v.y + w.y * v.x;
         t += l; if (t >= N) t -= N;
     }
-    out[((size_t)f * N + k) * N + l] = make_double2(ar, ai);
+    out[((size_t)f * M + k) * N + l] = make_double2(ar, ai);
 }
 
 // psi^[n] = Re(W^ - K Wmod^), K = W^[0,0]/Wmod^[0,0];  phi^ = Re(G^)
-__global__ void combine_filters_kernel(const double2* __restrict__ spec, int nwave, int N,
+__global__ void combine_filters_kernel(const double2* __restrict__ spec, int nwave, size_t NN,
                                        float* __restrict__ psi_hat, float* __restrict__ phi_hat) {
-    size_t NN = (size_t)N * N;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     int n = blockIdx.y;
     if (i >= NN) return;
@@ -127,9 +128,13 @@ const std::vector<CfgOps>& all_ops() {
 struct wst2d_plan {
     int device = 0;
     int H = 0, W = 0, J = 0, L = 0, max_order = 0;
-    int N = 0, K = 0, hout = 0;
+    int Hp = 0, Wp = 0, K = 0, hout = 0, wout = 0;   // padded size, coefficients, output map size
+    int N = 0;                        // padded side of the compiled (square) cascade; 0 for a generic plan
     int grid_max = 0;                 // persistent grid: SMs x resident CTAs per SM
-    const CfgOps* ops = nullptr;
+    const CfgOps* ops = nullptr;      // compiled fused cascade (wst_cascade.h), or
+    GenericPlan* gen = nullptr;       // the shape-generic DFT-matrix engine (wst_generic.cu)
+    int engine = 0;                   // WST2D_ENGINE_* actually in use
+    cudaMemPool_t pool = nullptr;     // private stream-ordered pool of this plan's device (scratch of forward calls)
     PlanTables pt{};
     float* d_tables = nullptr;
     std::vector<float> psi_hat, phi_hat;   // host copies (debug export)
@@ -161,35 +166,41 @@ struct DeviceGuard {
 };
 
 int build_filter_bank_gpu(wst2d_plan* p) {
-    const int N = p->N, J = p->J, L = p->L;
+    const int M = p->Hp, N = p->Wp, J = p->J, L = p->L;
     const int nwave = J * L, nf = 2 * nwave + 1;
-    const size_t NN = (size_t)N * N;
+    const size_t NN = (size_t)M * N;
     std::vector<GaborParams> gp(nf);
     bank_gabors(J, L, gp.data());
-    std::vector<double2> W(N);
-    for (int t = 0; t < N; ++t) {
-        double a = -2.0 * 3.14159265358979323846 * (double)t / (double)N;
-        W[t] = make_double2(std::cos(a), std::sin(a));
-    }
-    GaborParams* d_gp = nullptr; double2 *d_a = nullptr, *d_b = nullptr, *d_W = nullptr;
+    auto roots = [](int n) {
+        std::vector<double2> W(n);
+        for (int t = 0; t < n; ++t) {
+            double a = -2.0 * 3.14159265358979323846 * (double)t / (double)n;
+            W[t] = make_double2(std::cos(a), std::sin(a));
+        }
+        return W;
+    };
+    const std::vector<double2> W = roots(N), WM = roots(M);
+    GaborParams* d_gp = nullptr; double2 *d_a = nullptr, *d_b = nullptr, *d_W = nullptr, *d_WM = nullptr;
     float *d_psi = nullptr, *d_phi = nullptr;
-    auto cleanup = [&]() { cudaFree(d_gp); cudaFree(d_a); cudaFree(d_b); cudaFree(d_W); cudaFree(d_psi); cudaFree(d_phi); };
+    auto cleanup = [&]() { cudaFree(d_gp); cudaFree(d_a); cudaFree(d_b); cudaFree(d_W); cudaFree(d_WM); cudaFree(d_psi); cudaFree(d_phi); };
 #define TRYC(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); \
         return fail(WST2D_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
     TRYC(cudaMalloc(&d_gp, nf * sizeof(GaborParams)));
     TRYC(cudaMalloc(&d_a, nf * NN * sizeof(double2)));
     TRYC(cudaMalloc(&d_b, nf * NN * sizeof(double2)));
     TRYC(cudaMalloc(&d_W, N * sizeof(double2)));
+    TRYC(cudaMalloc(&d_WM, M * sizeof(double2)));
     TRYC(cudaMalloc(&d_psi, nwave * NN * sizeof(float)));
     TRYC(cudaMalloc(&d_phi, NN * sizeof(float)));
     TRYC(cudaMemcpy(d_gp, gp.data(), nf * sizeof(GaborParams), cudaMemcpyHostToDevice));
     TRYC(cudaMemcpy(d_W, W.data(), N * sizeof(double2), cudaMemcpyHostToDevice));
-    dim3 blk(128), grd((N + 127) / 128, N, nf);
-    gabor_spatial_kernel<<<grd, blk>>>(d_gp, nf, N, d_a);
-    dft_axis0_kernel<<<grd, blk>>>(d_a, d_b, d_W, N);
-    dft_axis1_kernel<<<grd, blk>>>(d_b, d_a, d_W, N);
+    TRYC(cudaMemcpy(d_WM, WM.data(), M * sizeof(double2), cudaMemcpyHostToDevice));
+    dim3 blk(128), grd((N + 127) / 128, M, nf);
+    gabor_spatial_kernel<<<grd, blk>>>(d_gp, nf, M, N, d_a);
+    dft_axis0_kernel<<<grd, blk>>>(d_a, d_b, d_WM, M, N);
+    dft_axis1_kernel<<<grd, blk>>>(d_b, d_a, d_W, M, N);
     dim3 cg((unsigned)((NN + 255) / 256), nwave + 1);
-    combine_filters_kernel<<<cg, 256>>>(d_a, nwave, N, d_psi, d_phi);
+    combine_filters_kernel<<<cg, 256>>>(d_a, nwave, NN, d_psi, d_phi);
     TRYC(cudaGetLastError());
     p->psi_hat.resize(nwave * NN);
     p->phi_hat.resize(NN);
@@ -226,6 +237,34 @@ __global__ void fma_peak_kernel(float* out, int iters) {
 // want the maps they live in a per-CTA scratch (grid x K*h*w floats, L2-resident) instead of HBM.
 // own_*: caller-provided scratch (host path) sized for grid_max CTAs; when NULL the scratch is stream-ordered
 // (cudaMallocAsync from the device's default pool).
+// One private stream-ordered memory pool per device, shared by the plans of that device: forward calls take their
+// scratch from it (cudaMallocFromPoolAsync) and it keeps freed blocks cached (release threshold = max) so that
+// steady-state calls never reach cudaMalloc.  The device's default pool is left untouched.
+cudaMemPool_t device_pool(int device) {
+    static std::mutex mu;
+    static std::vector<cudaMemPool_t> pools;
+    std::lock_guard<std::mutex> lk(mu);
+    if ((int)pools.size() <= device) pools.resize(device + 1, nullptr);
+    if (!pools[device]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        cudaMemPool_t pool = nullptr;
+        if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        pools[device] = pool;
+    }
+    return pools[device];
+}
+
+template <class T>
+cudaError_t pool_alloc(const wst2d_plan* p, T** ptr, size_t bytes, cudaStream_t st) {
+    return p->pool ? cudaMallocFromPoolAsync((void**)ptr, bytes, p->pool, st) : cudaMallocAsync((void**)ptr, bytes, st);
+}
+
 InputDesc plain_input(const void* ptr, int u8_channels) {
     InputDesc in{};
     in.ptr = ptr; in.mode = u8_channels > 0 ? 1 : 0; in.C = u8_channels > 0 ? u8_channels : 1;
@@ -236,18 +275,26 @@ int forward_impl(const wst2d_plan* p, const InputDesc& in, long long nsig, float
                  float* maps_dev, cudaStream_t st, cfloat* own_u0h = nullptr, float* own_maps = nullptr,
                  cfloat* own_ws = nullptr) {
     if (nsig == 0) return WST2D_OK;
-    const size_t map_elems = (size_t)p->K * p->hout * p->hout;
+    if (p->gen) {
+        std::string err;
+        prof_mark(p, p->prof_cascade, st);
+        cudaError_t ge = generic_forward(p->gen, in, nsig, feats_dev, maps_dev, st, err);
+        prof_mark(p, p->prof_cascade, st);
+        if (ge != cudaSuccess) return fail(WST2D_ERR_CUDA, "generic engine: " + err + ": " + cudaGetErrorString(ge));
+        return WST2D_OK;
+    }
+    const size_t map_elems = (size_t)p->K * p->hout * p->wout;
     const size_t u0h_elems = (size_t)p->N * (p->N / 2 + 1);
     const size_t ws_elems = p->ops->workspace_cfloats;
     const int grid = (int)(nsig < p->grid_max ? nsig : p->grid_max);
     cfloat* d_u0h = own_u0h; float* d_maps = own_maps; cfloat* d_ws = own_ws;
     cudaError_t e = cudaSuccess;
-    if (!d_u0h) e = cudaMallocAsync(&d_u0h, (size_t)grid * u0h_elems * sizeof(cfloat), st);
-    if (e == cudaSuccess && ws_elems && !d_ws) e = cudaMallocAsync(&d_ws, (size_t)grid * ws_elems * sizeof(cfloat), st);
-    if (e == cudaSuccess && !maps_dev && !d_maps) e = cudaMallocAsync(&d_maps, (size_t)grid * map_elems * sizeof(float), st);
+    if (!d_u0h) e = pool_alloc(p, &d_u0h, (size_t)grid * u0h_elems * sizeof(cfloat), st);
+    if (e == cudaSuccess && ws_elems && !d_ws) e = pool_alloc(p, &d_ws, (size_t)grid * ws_elems * sizeof(cfloat), st);
+    if (e == cudaSuccess && !maps_dev && !d_maps) e = pool_alloc(p, &d_maps, (size_t)grid * map_elems * sizeof(float), st);
     int rc = WST2D_OK;
     if (e != cudaSuccess) {
-        rc = fail(WST2D_ERR_CUDA, std::string("cudaMallocAsync(scratch): ") + cudaGetErrorString(e));
+        rc = fail(WST2D_ERR_CUDA, std::string("stream-ordered scratch allocation: ") + cudaGetErrorString(e));
     } else {
         prof_mark(p, p->prof_cascade, st);
         e = p->ops->launch(p->pt, in, nsig, d_u0h, d_ws, maps_dev, maps_dev ? nullptr : d_maps, feats_dev, grid, st);
@@ -267,23 +314,32 @@ extern "C" {
 const char* wst2d_last_error(void) { return g_last_error.c_str(); }
 const char* wst2d_version(void) { return "wst_b200 0.1 (sm_100a)"; }
 
-int wst2d_plan_create(wst2d_plan** out, int device, int H, int W, int J, int L, int max_order) {
+int wst2d_plan_create_ex(wst2d_plan** out, int device, int H, int W, int J, int L, int max_order, int engine) {
     if (!out) return fail(WST2D_ERR_ARG, "out is NULL");
     *out = nullptr;
     if (H <= 0 || W <= 0 || J < 1 || J >= kMaxJ || L < 1 || L > 64 || (max_order != 1 && max_order != 2))
         return fail(WST2D_ERR_ARG, "invalid plan arguments");
+    if (engine < WST2D_ENGINE_AUTO || engine > WST2D_ENGINE_GEMM_TF32X3) return fail(WST2D_ERR_ARG, "unknown engine");
     if ((1 << J) > H || (1 << J) > W)
         return fail(WST2D_ERR_ARG, "The smallest dimension should be larger than 2^J.");
-    if (L > kMaxL) return fail(WST2D_ERR_UNSUPPORTED, "more than 8 orientations (L) is not supported by the compiled cascades");
+    if (const char* ev = getenv("WST_ENGINE")) {           // tuning / A-B runs: "fft", "gemm", "gemm_tf32x3"
+        if (engine == WST2D_ENGINE_AUTO) {
+            if (!strcmp(ev, "gemm")) engine = WST2D_ENGINE_GEMM_SIMT;
+            else if (!strcmp(ev, "gemm_tf32x3")) engine = WST2D_ENGINE_GEMM_TF32X3;
+            else if (!strcmp(ev, "fft")) engine = WST2D_ENGINE_FFT;
+        }
+    }
     const int Hp = padded_size(H, J), Wp = padded_size(W, J);
     const CfgOps* ops = nullptr;
-    if (Hp == Wp)
+    if (Hp == Wp && L <= kMaxL && (engine == WST2D_ENGINE_AUTO || engine == WST2D_ENGINE_FFT))
         for (const CfgOps& o : all_ops()) if (o.N == Hp && o.J == J) { ops = &o; break; }
-    if (!ops) {
+    if (!ops && engine == WST2D_ENGINE_FFT) {
         char buf[160];
-        snprintf(buf, sizeof buf, "no compiled cascade for padded size %dx%d, J=%d", Hp, Wp, J);
+        snprintf(buf, sizeof buf, "no compiled cascade for padded size %dx%d, J=%d, L=%d", Hp, Wp, J, L);
         return fail(WST2D_ERR_UNSUPPORTED, buf);
     }
+    if ((Hp - H + 1) / 2 >= H || (Wp - W + 1) / 2 >= W)
+        return fail(WST2D_ERR_UNSUPPORTED, "reflect padding as wide as the image (H or W equal to 2^J) is not supported");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -293,10 +349,24 @@ int wst2d_plan_create(wst2d_plan** out, int device, int H, int W, int J, int L, 
 
     wst2d_plan* p = new wst2d_plan();
     p->device = device; p->H = H; p->W = W; p->J = J; p->L = L; p->max_order = max_order;
-    p->N = Hp; p->K = num_coefficients(J, L, max_order); p->hout = ops->hout; p->ops = ops;
+    p->Hp = Hp; p->Wp = Wp; p->K = num_coefficients(J, L, max_order);
+    p->hout = (Hp >> J) - 2; p->wout = (Wp >> J) - 2;
+    p->N = ops ? Hp : 0; p->ops = ops;
+    p->engine = ops ? WST2D_ENGINE_FFT : (engine == WST2D_ENGINE_GEMM_TF32X3 ? WST2D_ENGINE_GEMM_TF32X3 : WST2D_ENGINE_GEMM_SIMT);
+    p->pool = device_pool(device);
 
     int rc = build_filter_bank_gpu(p);
     if (rc != WST2D_OK) { delete p; return rc; }
+
+    if (!ops) {
+        std::string err;
+        int grc = generic_create(&p->gen, device, H, W, J, L, max_order,
+                                 p->engine == WST2D_ENGINE_GEMM_TF32X3 ? kEngineTf32x3 : kEngineSimt,
+                                 p->psi_hat.data(), p->phi_hat.data(), err);
+        if (grc != 0) { delete p; return fail(grc == -2 ? WST2D_ERR_UNSUPPORTED : grc == -3 ? WST2D_ERR_CUDA : WST2D_ERR_ARG, err); }
+        *out = p;
+        return WST2D_OK;
+    }
 
     std::vector<float> buf; TableOffsets off; std::string err;
     if (!ops->build(L, p->psi_hat.data(), p->phi_hat.data(), buf, off, err)) { delete p; return fail(WST2D_ERR_ARG, err); }
@@ -318,15 +388,17 @@ int wst2d_plan_create(wst2d_plan** out, int device, int H, int W, int J, int L, 
         return fail(WST2D_ERR_CUDA, "cascade kernel setup: " + m);
     }
     p->grid_max = slots;
-    {   // keep the stream-ordered scratch (cudaMallocAsync in forward) cached across synchronisations
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-            unsigned long long thr = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-        }
-    }
     *out = p;
     return WST2D_OK;
+}
+
+int wst2d_plan_create(wst2d_plan** out, int device, int H, int W, int J, int L, int max_order) {
+    return wst2d_plan_create_ex(out, device, H, W, J, L, max_order, WST2D_ENGINE_AUTO);
+}
+
+int wst2d_plan_engine(const wst2d_plan* p) {
+    if (!p) return fail(WST2D_ERR_ARG, "plan is NULL");
+    return p->engine;
 }
 
 int wst2d_plan_destroy(wst2d_plan* plan) {
@@ -338,6 +410,7 @@ int wst2d_plan_destroy(wst2d_plan* plan) {
         cudaFree(plan->host.ws[i]);
     }
     cudaFree(plan->d_tables);
+    generic_destroy(plan->gen);
     delete plan;
     return WST2D_OK;
 }
@@ -346,9 +419,9 @@ int wst2d_query(const wst2d_plan* p, int* K, int* h, int* w, int* Hp, int* Wp) {
     if (!p) return fail(WST2D_ERR_ARG, "plan is NULL");
     if (K) *K = p->K;
     if (h) *h = p->hout;
-    if (w) *w = p->hout;
-    if (Hp) *Hp = p->N;
-    if (Wp) *Wp = p->N;
+    if (w) *w = p->wout;
+    if (Hp) *Hp = p->Hp;
+    if (Wp) *Wp = p->Wp;
     return WST2D_OK;
 }
 
@@ -403,9 +476,9 @@ int wst2d_forward_host(const wst2d_plan* p, const float* x_host, int64_t B, int 
     wst2d_plan::HostPath& hp = p->host;
     std::lock_guard<std::mutex> lk(hp.mu);
     const size_t sig_in = (size_t)p->H * p->W, sig_out = (size_t)2 * p->K;
-    const size_t map_elems = (size_t)p->K * p->hout * p->hout;
+    const size_t map_elems = (size_t)p->K * p->hout * p->wout;
     // chunk: a few persistent-grid waves per copy so that H2D, compute and D2H of neighbouring chunks overlap
-    long long chunk_sig = (long long)p->grid_max * 6;
+    long long chunk_sig = p->gen ? 1024 : (long long)p->grid_max * 6;
     if (const char* ev = getenv("WST_HOST_CHUNK_SIGNALS")) chunk_sig = atoll(ev);
     chunk_sig = chunk_sig / C * C;
     if (chunk_sig < C) chunk_sig = C;
@@ -421,6 +494,7 @@ int wst2d_forward_host(const wst2d_plan* p, const float* x_host, int64_t B, int 
             if (!hp.st[i]) CUDA_TRY(cudaStreamCreateWithFlags(&hp.st[i], cudaStreamNonBlocking));
             CUDA_TRY(cudaMalloc(&hp.x[i], chunk_sig * sig_in * sizeof(float)));
             CUDA_TRY(cudaMalloc(&hp.f[i], chunk_sig * sig_out * sizeof(float)));
+            if (p->gen) continue;                  // the generic engine takes its workspace from the plan's pool
             CUDA_TRY(cudaMalloc(&hp.u0h[i], (size_t)p->grid_max * p->N * (p->N / 2 + 1) * sizeof(cfloat)));
             CUDA_TRY(cudaMalloc(&hp.maps[i], (size_t)p->grid_max * map_elems * sizeof(float)));
             if (p->ops->workspace_cfloats)
@@ -519,12 +593,13 @@ int wst2d_debug_phase_cycles(const wst2d_plan* p, const float* x_dev, int64_t ns
     if (!p || !x_dev || !cycles_host) return fail(WST2D_ERR_ARG, "NULL argument");
     if (ntags != kNumPhaseTags) return fail(WST2D_ERR_ARG, "ntags must be " + std::to_string(kNumPhaseTags));
     if (nsig <= 0) return fail(WST2D_ERR_ARG, "nsig must be positive");
+    if (!p->ops) return fail(WST2D_ERR_UNSUPPORTED, "phase cycles exist for the fused cascades only");
     DeviceGuard guard(p->device);
     const int grid = (int)(nsig < p->grid_max ? nsig : p->grid_max);
     cfloat* d_u0h = nullptr; float* d_maps = nullptr; long long* d_cyc = nullptr; cfloat* d_ws = nullptr;
     CUDA_TRY(cudaMalloc(&d_u0h, (size_t)grid * p->N * (p->N / 2 + 1) * sizeof(cfloat)));
     if (p->ops->workspace_cfloats) CUDA_TRY(cudaMalloc(&d_ws, (size_t)grid * p->ops->workspace_cfloats * sizeof(cfloat)));
-    CUDA_TRY(cudaMalloc(&d_maps, (size_t)grid * p->K * p->hout * p->hout * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&d_maps, (size_t)grid * p->K * p->hout * p->wout * sizeof(float)));
     float* d_feats = nullptr;
     CUDA_TRY(cudaMalloc(&d_feats, (size_t)nsig * 2 * p->K * sizeof(float)));
     CUDA_TRY(cudaMalloc(&d_cyc, kNumPhaseTags * sizeof(long long)));
@@ -538,7 +613,10 @@ int wst2d_debug_phase_cycles(const wst2d_plan* p, const float* x_dev, int64_t ns
 
 int wst2d_launch_count(const wst2d_plan* p, int64_t B, int C) {
     if (!p) return fail(WST2D_ERR_ARG, "plan is NULL");
+    if (p->gen) return (int)generic_launch_count(p->gen, (long long)B * C);
     return (long long)B * C > 0 ? 1 : 0;   // one fused cascade + pooling kernel per forward call
 }
+
+int wst2d_debug_num_phase_tags(void) { return kNumPhaseTags; }
 
 }  // extern "C"

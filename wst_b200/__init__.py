@@ -13,3 +13,4 @@ __path__.insert(0, _real)
 from ._api import *  # noqa: E402,F401,F403
 from ._api import __all__  # noqa: E402,F401
 from . import numpy, torch  # noqa: E402,F401  kymatio-style frontends: wst_b200.numpy.Scattering2D, wst_b200.torch.Scattering2D
+from . import _ops  # noqa: E402,F401  registers torch.ops.wst.scattering2d_features / scattering2d_maps
