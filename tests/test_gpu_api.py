@@ -94,8 +94,11 @@ def test_forward_host_validates_out(wst):
             plan.forward_host(x, out=bad)
     out = np.empty((2, 3, 2, 81), np.float32)
     assert plan.forward_host(x, out=out) is out
-    with pytest.raises(RuntimeError, match="cuda:0"):
-        plan.forward(torch.zeros((1, 32, 32, 3), dtype=torch.uint8))     # uint8 path checks the device too
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        plan.forward(torch.zeros((1, 32, 32, 3), dtype=torch.uint8))     # uint8 path validates where the pixels live
+    if torch.cuda.device_count() > 1:
+        with pytest.raises(RuntimeError, match="cuda:0"):
+            plan.forward(torch.zeros((1, 32, 32, 3), dtype=torch.uint8, device="cuda:1"))
 
 
 def test_torch_library_op(wst):

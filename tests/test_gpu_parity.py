@@ -240,8 +240,11 @@ def test_edge_cases(wst):
     assert np.abs(m[1:]).max() < 1e-5 * c
     with pytest.raises(RuntimeError, match="spatial size"):
         plan.forward(torch.rand(1, 1, 16, 16, device="cuda"))
-    with pytest.raises(NotImplementedError):
-        wst.get_plan(100, 100, 2, 8)
+    with pytest.raises(NotImplementedError):                  # the fused cascades are compiled per padded side ...
+        wst.Plan(100, 100, 2, 8, engine="fft")
+    assert wst.get_plan(100, 100, 2, 8).engine == "gemm"     # ... every other shape runs on the DFT-matrix engine
+    with pytest.raises(NotImplementedError, match="as wide as the image"):
+        wst.get_plan(16, 40, 4, 8)                            # kymatio's pad == image special case
 
 
 def test_u8_ingest_equals_float_path(wst):
