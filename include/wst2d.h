@@ -128,6 +128,9 @@ const char* wst2d_noise_last_error(void);
  * feats_host [B][C][2][K] live in host memory (pinned for full overlap); copies are chunked and
  * double-buffered against compute on two internal streams.  Synchronous on return. */
 int wst2d_forward_host(const wst2d_plan* plan, const float* x_host, int64_t B, int C, float* feats_host);
+/* Same from uint8 pixels as PIL delivers them, x_host [B][H][W][C] (load_rgb_image's input,
+ * src/training/train_and_save_model.py:51-56): a quarter of the host-to-device bytes. */
+int wst2d_forward_host_u8(const wst2d_plan* plan, const uint8_t* x_host, int64_t B, int C, float* feats_host);
 
 /* Debug/test export of the plan's full-resolution Fourier-domain filters, host pointers:
  * psi_hat [J*L][Hp][Wp], phi_hat [Hp][Wp]; either may be NULL. */

@@ -117,3 +117,26 @@ def test_torch_library_op(wst):
     compiled = torch.compile(lambda t: torch.ops.wst.scattering2d_features(t, 3, 8, 2, 0, False) * 2.0, fullgraph=True,
                              backend="aot_eager")          # Dynamo traces through the op (fake kernel), no graph break
     assert torch.allclose(compiled(x), a * 2.0)
+
+
+@pytest.mark.parametrize("M,J,B", [(128, 2, 1), (128, 4, 2), (64, 3, 5), (32, 2, 1)])
+def test_small_batches_split_signals_across_ctas(wst, M, J, B):
+    """The reference calls the extractor one image at a time (train_and_save_model.py:486-488): with fewer signals than
+    SMs the first-order groups of a signal are shared among several CTAs and the last one pools.  Same numbers as the
+    one-CTA-per-signal path, bit for bit (the arithmetic of every group is unchanged)."""
+    import os
+    rng = np.random.default_rng(M + J + B)
+    x = torch.from_numpy((rng.integers(0, 256, (B, 3, M, M)) / 255.0).astype(np.float32)).cuda()
+    plan = wst.get_plan(M, M, J)
+    f_split, m_split = plan.forward(x, True, True)
+    f_only = plan.forward(x)[0]                       # maps in the per-signal scratch
+    os.environ["WST_NO_SPLIT"] = "1"
+    try:
+        f_ref, m_ref = plan.forward(x, True, True)
+    finally:
+        del os.environ["WST_NO_SPLIT"]
+    torch.cuda.synchronize()
+    assert torch.equal(m_split, m_ref)
+    assert torch.equal(f_split, f_ref) and torch.equal(f_only, f_ref)
+    one = wst.extract_wst_features(x[0].cpu().numpy(), J=J)                 # host path, one image
+    assert np.array_equal(one, f_ref[0].reshape(-1).cpu().numpy())

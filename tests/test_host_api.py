@@ -81,6 +81,17 @@ def _gather_worker(rank, world, port, B, F, out_dir):
     full = torch.arange(B * F, dtype=torch.float32).reshape(B, F)
     lo, hi = wst_b200.shard_range(B, rank, world)
     got = wst_b200.gather_features(full[lo:hi].clone(), B)
+    if B % world == 0:                       # equal shards: the asynchronous form into a caller-provided matrix
+        out = torch.full((B, F), -1.0)
+        res, work = wst_b200.gather_features(full[lo:hi].clone(), B, async_op=True, out=out)
+        work.wait()
+        assert res is out and torch.equal(out, got)
+    else:
+        try:
+            wst_b200.gather_features(full[lo:hi].clone(), B, async_op=True)
+            raise AssertionError("ragged async gather must be refused")
+        except ValueError:
+            pass
     torch.save(got, os.path.join(out_dir, "r%d.pt" % rank))
     dist.destroy_process_group()
 

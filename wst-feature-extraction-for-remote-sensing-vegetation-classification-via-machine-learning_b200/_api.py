@@ -166,8 +166,9 @@ class Plan:
 
     # -- host path ---------------------------------------------------------------------------
     def forward_host(self, x, out=None):
-        """x: [B, C, H, W] float32 C-contiguous numpy array or CPU tensor (pinned for full overlap)
-        -> feats [B, C, 2, K] numpy float32.  Copies are chunked and overlapped inside the library."""
+        """x: [B, C, H, W] float32 (or [B, H, W, C] uint8, PIL / load_rgb_image order) C-contiguous numpy array or CPU
+        tensor (pinned for full overlap) -> feats [B, C, 2, K] numpy float32.  Copies are chunked and overlapped inside
+        the library."""
         lib = _lib.load()
         if isinstance(x, torch.Tensor):
             if x.is_cuda:
@@ -175,11 +176,14 @@ class Plan:
             xa = x.numpy()
         else:
             xa = x
-        if not isinstance(xa, np.ndarray) or xa.dtype != np.float32 or not xa.flags["C_CONTIGUOUS"] or xa.ndim != 4:
-            raise RuntimeError("forward_host expects a C-contiguous float32 [B, C, H, W] array.")
-        if xa.shape[-2] != self.H or xa.shape[-1] != self.W:
+        if not isinstance(xa, np.ndarray) or xa.dtype not in (np.float32, np.uint8) or not xa.flags["C_CONTIGUOUS"] \
+                or xa.ndim != 4:
+            raise RuntimeError("forward_host expects a C-contiguous float32 [B, C, H, W] (or uint8 [B, H, W, C]) array.")
+        u8 = xa.dtype == np.uint8
+        hh, ww = (xa.shape[1], xa.shape[2]) if u8 else (xa.shape[-2], xa.shape[-1])
+        if hh != self.H or ww != self.W:
             raise RuntimeError("NumPy array must be of spatial size (%i,%i)." % (self.H, self.W))
-        B, C = xa.shape[0], xa.shape[1]
+        B, C = (xa.shape[0], xa.shape[3]) if u8 else (xa.shape[0], xa.shape[1])
         if out is None:
             out = np.empty((B, C, 2, self.K), np.float32)
         if isinstance(out, torch.Tensor):
@@ -192,7 +196,8 @@ class Plan:
                 and oa.flags["WRITEABLE"] and tuple(oa.shape) == (B, C, 2, self.K)):
             raise RuntimeError("forward_host: `out` must be a writeable C-contiguous float32 array of shape "
                                "(%d, %d, 2, %d)." % (B, C, self.K))
-        _lib.check(lib.wst2d_forward_host(self._h, xa.ctypes.data, B, C, oa.ctypes.data))
+        fn = lib.wst2d_forward_host_u8 if u8 else lib.wst2d_forward_host
+        _lib.check(fn(self._h, xa.ctypes.data, B, C, oa.ctypes.data))
         return out
 
     def filters(self):

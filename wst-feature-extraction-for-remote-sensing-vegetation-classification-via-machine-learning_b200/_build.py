@@ -10,9 +10,13 @@ import subprocess
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
-OBJ = os.path.join(PKG_DIR, "_obj")
+import hashlib
+
+# Tuning builds (WST_BUILD_DEFS="-DWST_OPT_X=0 ..." with WST_BUILD_LIB naming the output) keep their objects apart
+_DEFS = os.environ.get("WST_BUILD_DEFS", "").split()
+OBJ = os.path.join(PKG_DIR, "_obj", hashlib.sha1(" ".join(_DEFS).encode()).hexdigest()[:8] if _DEFS else "default")
 LIB_PATH = os.path.join(PKG_DIR, os.environ.get("WST_BUILD_LIB", "libwst_b200.so"))
-NVCC_FLAGS = os.environ.get("WST_BUILD_DEFS", "").split() + ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
+NVCC_FLAGS = _DEFS + ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC"]
 # The global-workspace variant (CFGG entries: sides whose arrays do not fit in shared memory): threads per CTA (two
 # CTAs share an SM), CTAs per cluster (1: one CTA per signal; the cluster form is kept as a tuning knob, it measured
@@ -36,9 +40,10 @@ for _item in filter(None, os.environ.get("WST_BUILD_SHARED", "").split(",")):
 def configs():
     """[(N, J, global_workspace)] from csrc/wst_configs.inc."""
     out = []
+    only = os.environ.get("WST_BUILD_ONLY")          # tuning builds: "160:4,80:3" compiles those cascades only
     for line in open(os.path.join(CSRC, "wst_configs.inc")):
         m = re.match(r"\s*(CFGG?)\((\d+),\s*(\d+)\)", line)
-        if m:
+        if m and (not only or "%s:%s" % (m.group(2), m.group(3)) in only.split(",")):
             out.append((int(m.group(2)), int(m.group(3)), m.group(1) == "CFGG"))
     return out
 
@@ -74,6 +79,12 @@ def build_library(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "nvcc")
     os.makedirs(OBJ, exist_ok=True)
     extra = ["-Xptxas", "-v"] if verbose else []
+    if os.environ.get("WST_BUILD_ONLY"):             # filtered copy of the configuration list for wst_lib.cu / wst_ops.h
+        inc = os.path.join(OBJ, "wst_configs_only.inc")
+        lines = ["%s(%d, %d)\n" % ("CFGG" if g else "CFG", n, j) for n, j, g in configs()]
+        if not os.path.exists(inc) or open(inc).read() != "".join(lines):
+            open(inc, "w").write("".join(lines))
+        extra += ['-DWST_CONFIGS_FILE="%s"' % inc]
     jobs, objs = [], []
     o = os.path.join(OBJ, "wst_lib.o")
     objs.append(o)

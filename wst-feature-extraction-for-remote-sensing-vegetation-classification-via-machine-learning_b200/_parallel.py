@@ -24,27 +24,40 @@ def shard_sizes(B, world_size):
     return [shard_range(B, r, world_size)[1] - shard_range(B, r, world_size)[0] for r in range(world_size)]
 
 
-def gather_features(local_feats, B, group=None):
-    """All-gather ragged row shards [b_r, F] into [B, F] in rank (= input) order.
+def gather_features(local_feats, B, group=None, async_op=False, out=None):
+    """All-gather row shards [b_r, F] into [B, F] in rank (= input) order.
 
-    Works on whatever device `local_feats` lives on: NCCL for CUDA tensors, gloo for CPU tensors
-    (the CPU form is what the world_size-2 tests exercise).  Shards are padded to the largest
-    shard so a single all_gather_into_tensor suffices.
-    """
+    Works on whatever device `local_feats` lives on: NCCL for CUDA tensors, gloo for CPU tensors (the CPU form is what
+    the world_size-2 tests exercise).  Equal shards (B divisible by the world size — the benchmark's case) are gathered
+    straight into the output matrix by one all_gather_into_tensor: no padding copy, no concatenation.  Ragged shards
+    are padded to the largest shard, gathered, and compacted.
+
+    async_op=True (equal shards only) returns (out, work): the collective runs on the backend's own stream, so the
+    caller can launch the next batch's kernels while the gather is in flight, and calls work.wait() before reading
+    `out` (which may be passed in to reuse a buffer)."""
     if not dist.is_available() or not dist.is_initialized():
         if local_feats.shape[0] != B:
             raise ValueError("not distributed: local shard must be the whole batch")
-        return local_feats
+        return (local_feats, None) if async_op else local_feats
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     sizes = shard_sizes(B, world)
     if local_feats.shape[0] != sizes[rank]:
         raise ValueError("rank %d holds %d rows, expected %d" % (rank, local_feats.shape[0], sizes[rank]))
     F = local_feats.shape[1]
+    if min(sizes) == max(sizes):
+        if out is None:
+            out = local_feats.new_empty((B, F))
+        elif tuple(out.shape) != (B, F) or not out.is_contiguous():
+            raise ValueError("out must be a contiguous [B, F] tensor")
+        work = dist.all_gather_into_tensor(out, local_feats.contiguous(), group=group, async_op=async_op)
+        return (out, work) if async_op else out
+    if async_op:
+        raise ValueError("async_op needs equal shards (B divisible by the world size)")
     mx = max(sizes)
     padded = local_feats.new_zeros((mx, F))
     padded[: sizes[rank]] = local_feats
-    out = local_feats.new_empty((world * mx, F))
-    dist.all_gather_into_tensor(out, padded.contiguous(), group=group)
-    out = out.view(world, mx, F)
-    return torch.cat([out[r, : sizes[r]] for r in range(world)], dim=0)
+    buf = local_feats.new_empty((world * mx, F))
+    dist.all_gather_into_tensor(buf, padded, group=group)
+    buf = buf.view(world, mx, F)
+    return torch.cat([buf[r, : sizes[r]] for r in range(world)], dim=0)

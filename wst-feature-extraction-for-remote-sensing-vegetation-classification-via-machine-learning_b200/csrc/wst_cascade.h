@@ -138,6 +138,31 @@ WST_CX bool lp_banded(int m, int hout, int level) {
 #ifndef WST_STAGE_BUFS
 #define WST_STAGE_BUFS 1
 #endif
+// Tuning knobs of the shared-memory cascade (A/B builds: tools/tune_variants.sh):
+//   WST_OPT_HOIST  task loops whose thread stride is a multiple of the line count keep the line / column index of a
+//                  thread fixed across iterations (no per-iteration div / mod, row-independent addressing hoisted)
+//   WST_OPT_BATCH  radix passes with short butterflies take two tasks per iteration (loads of both, butterflies of
+//                  both, stores of both): twice the independent work per thread between shared-memory round trips
+//   WST_OPT_TMA    the H x W input of the NEXT signal is fetched by bulk asynchronous copies (TMA, cp.async.bulk +
+//                  mbarrier) into a free part of shared memory while the last level of the current signal runs
+#ifndef WST_OPT_HOIST
+#define WST_OPT_HOIST 0
+#endif
+//   WST_OPT_HOIST_PROD  the same for the filter products only
+//   WST_OPT_PREFETCH    dense two-orientation products issue the filter loads of a thread's next output pair before
+//                       the arithmetic of the current one (L2 latency overlaps the shared-memory reads and FMAs)
+#ifndef WST_OPT_HOIST_PROD
+#define WST_OPT_HOIST_PROD WST_OPT_HOIST
+#endif
+#ifndef WST_OPT_PREFETCH
+#define WST_OPT_PREFETCH 0
+#endif
+#ifndef WST_OPT_BATCH
+#define WST_OPT_BATCH 0
+#endif
+#ifndef WST_OPT_TMA
+#define WST_OPT_TMA 1
+#endif
 #ifndef WST_STAGE_TC_MAX
 #define WST_STAGE_TC_MAX 16
 #endif
@@ -369,6 +394,32 @@ template <int CL> struct ProfExec {
     }
 };
 #endif
+// ------------------------------------------------------------------ bulk asynchronous copies (TMA) + mbarrier
+// cp.async.bulk moves a contiguous run of bytes global -> shared without passing through registers and signals an
+// mbarrier with the byte count; the waiting threads spin on the barrier's phase parity.  Used to fetch the next
+// signal's pixels while the current signal is still being transformed (Cascade::prefetch_input).
+#ifdef __CUDACC__
+WST_D unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+WST_D void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+WST_D void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+WST_D void tma_bulk_g2s(void* dst_shared, const void* src_global, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_shared)), "l"(src_global), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+WST_D void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+WST_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
+
 template <int NT> struct HostExec {
     template <int TAG, class F> void phase(F&& f) { for (int t = 0; t < NT; ++t) f(t); }
 };
@@ -385,14 +436,10 @@ template <int M, int DIR, bool TW, int NL, int LS, int ES, int NT, bool SUBFAST 
 WST_D void pass_strided(int tid, cfloat* base, int narr, int AS, const cfloat* tw) {
     constexpr int R1 = Fft1<M>::R1, R2 = Fft1<M>::R2;
     const int total = narr * R2 * NL;
-    for (int b = tid; b < total; b += NT) {
-        int line, i2, g;
-        if constexpr (SUBFAST) { i2 = b % R2; int r = b / R2; line = r % NL; g = r / NL; }
-        else { line = b % NL; int r = b / NL; i2 = r % R2; g = r / R2; }
-        cfloat* p = base + g * AS + line * LS + i2 * ES;
-        cfloat a[R1];
+    auto load = [&](cfloat* p, cfloat (&a)[R1]) {
         static_for<0, R1>([&](auto K) { constexpr int k = decltype(K)::value; a[k] = p[k * R2 * ES]; });
-        dft<R1, DIR>(a);
+    };
+    auto store = [&](cfloat* p, int i2, cfloat (&a)[R1]) {
         static_for<0, R1>([&](auto K) {
             constexpr int k = decltype(K)::value;
             cfloat v = a[k];
@@ -402,6 +449,46 @@ WST_D void pass_strided(int tid, cfloat* base, int narr, int AS, const cfloat* t
             }
             p[k * R2 * ES] = v;
         });
+    };
+    if constexpr (WST_OPT_HOIST && !SUBFAST && NT % NL == 0) {
+        // the thread's line is the same in every iteration; r = (array, sub-butterfly) advances by NT / NL
+        constexpr int STEP = NT / NL;
+        cfloat* pl = base + (tid % NL) * LS;
+        const int rtot = narr * R2;
+        if constexpr (WST_OPT_BATCH && R1 <= 8) {
+            for (int r = tid / NL; r < rtot; r += 2 * STEP) {
+                const bool two = r + STEP < rtot;
+                const int rb = two ? r + STEP : r;
+                const int i2a = r % R2, i2b = rb % R2;
+                cfloat* pa = pl + (r / R2) * AS + i2a * ES;
+                cfloat* pb = pl + (rb / R2) * AS + i2b * ES;
+                cfloat a[R1], c[R1];
+                load(pa, a); load(pb, c);
+                dft<R1, DIR>(a); dft<R1, DIR>(c);
+                store(pa, i2a, a);
+                if (two) store(pb, i2b, c);
+            }
+        } else {
+            for (int r = tid / NL; r < rtot; r += STEP) {
+                const int i2 = r % R2;
+                cfloat* p = pl + (r / R2) * AS + i2 * ES;
+                cfloat a[R1];
+                load(p, a);
+                dft<R1, DIR>(a);
+                store(p, i2, a);
+            }
+        }
+        return;
+    }
+    for (int b = tid; b < total; b += NT) {
+        int line, i2, g;
+        if constexpr (SUBFAST) { i2 = b % R2; int r = b / R2; line = r % NL; g = r / NL; }
+        else { line = b % NL; int r = b / NL; i2 = r % R2; g = r / R2; }
+        cfloat* p = base + g * AS + line * LS + i2 * ES;
+        cfloat a[R1];
+        load(p, a);
+        dft<R1, DIR>(a);
+        store(p, i2, a);
     }
 }
 
@@ -410,14 +497,10 @@ template <int M, int DIR, bool TW, int NL, int LS, int ES, int NT, bool SUBFAST 
 WST_D void pass_contig(int tid, cfloat* base, int narr, int AS, const cfloat* tw) {
     constexpr int R1 = Fft1<M>::R1, R2 = Fft1<M>::R2;
     const int total = narr * R1 * NL;
-    for (int b = tid; b < total; b += NT) {
-        int line, k1, g;
-        if constexpr (SUBFAST) { k1 = b % R1; int r = b / R1; line = r % NL; g = r / NL; }
-        else { line = b % NL; int r = b / NL; k1 = r % R1; g = r / R1; }
-        cfloat* p = base + g * AS + line * LS + k1 * R2 * ES;
-        cfloat v[R2];
+    auto load = [&](cfloat* p, cfloat (&v)[R2]) {
         static_for<0, R2>([&](auto I) { constexpr int i = decltype(I)::value; v[i] = p[i * ES]; });
-        dft<R2, DIR>(v);
+    };
+    auto store = [&](cfloat* p, int k1, cfloat (&v)[R2]) {
         static_for<0, R2>([&](auto I) {
             constexpr int i = decltype(I)::value;
             cfloat o = v[i];
@@ -427,6 +510,45 @@ WST_D void pass_contig(int tid, cfloat* base, int narr, int AS, const cfloat* tw
             }
             p[i * ES] = o;
         });
+    };
+    if constexpr (WST_OPT_HOIST && !SUBFAST && NT % NL == 0) {
+        constexpr int STEP = NT / NL;
+        cfloat* pl = base + (tid % NL) * LS;
+        const int rtot = narr * R1;
+        if constexpr (WST_OPT_BATCH && R2 <= 10) {
+            for (int r = tid / NL; r < rtot; r += 2 * STEP) {
+                const bool two = r + STEP < rtot;
+                const int rb = two ? r + STEP : r;
+                const int k1a = r % R1, k1b = rb % R1;
+                cfloat* pa = pl + (r / R1) * AS + k1a * R2 * ES;
+                cfloat* pb = pl + (rb / R1) * AS + k1b * R2 * ES;
+                cfloat v[R2], u[R2];
+                load(pa, v); load(pb, u);
+                dft<R2, DIR>(v); dft<R2, DIR>(u);
+                store(pa, k1a, v);
+                if (two) store(pb, k1b, u);
+            }
+        } else {
+            for (int r = tid / NL; r < rtot; r += STEP) {
+                const int k1 = r % R1;
+                cfloat* p = pl + (r / R1) * AS + k1 * R2 * ES;
+                cfloat v[R2];
+                load(p, v);
+                dft<R2, DIR>(v);
+                store(p, k1, v);
+            }
+        }
+        return;
+    }
+    for (int b = tid; b < total; b += NT) {
+        int line, k1, g;
+        if constexpr (SUBFAST) { k1 = b % R1; int r = b / R1; line = r % NL; g = r / NL; }
+        else { line = b % NL; int r = b / NL; k1 = r % R1; g = r / R1; }
+        cfloat* p = base + g * AS + line * LS + k1 * R2 * ES;
+        cfloat v[R2];
+        load(p, v);
+        dft<R2, DIR>(v);
+        store(p, k1, v);
     }
 }
 
@@ -468,9 +590,12 @@ WST_D void pass_rows_final(int tid, cfloat* base, int narr, int AS, const float*
     constexpr int YS = (R1 > 1) ? R2 : 1;             // their stride along y
     const int nsub = (R1 > 1) ? R2 : 1;
     const int total = narr * nsub * HALF;
-    for (int b = tid; b < total; b += NT) {
+    // HOIST: the thread's row pair is the same in every iteration, b = (array, sub-butterfly) advances by NT / HALF
+    constexpr bool HOIST = WST_OPT_HOIST && !SUBFAST && NT % HALF == 0;
+    for (int b = HOIST ? tid / HALF : tid; b < (HOIST ? narr * nsub : total); b += (HOIST ? NT / HALF : NT)) {
         int x, i2, g;
-        if constexpr (SUBFAST) { i2 = b % nsub; int r = b / nsub; x = r % HALF; g = r / HALF; }
+        if constexpr (HOIST) { x = tid % HALF; i2 = b % nsub; g = b / nsub; }
+        else if constexpr (SUBFAST) { i2 = b % nsub; int r = b / nsub; x = r % HALF; g = r / HALF; }
         else { x = b % HALF; int r = b / HALF; i2 = r % nsub; g = r / nsub; }
         cfloat* p0 = base + g * AS + x * P + i2;
         cfloat* p1 = p0 + POFF;
@@ -816,14 +941,47 @@ WST_D void product_fold(int tid, const cfloat* uh, const float* filt, int rows, 
         // one or two arrays fit): these phases are issue-bound and the index arithmetic is shared by only GS
         // accumulators, so each thread takes two adjacent outputs (l even, l+1): one 8/16-byte filter load and
         // one row/mirror computation serve both.
-        constexpr int HM = MP / 2, PH = MP / 2 + 1;
-        for (int o = tid; o < MC * (MC / 2); o += NT) {
-            const int lc = (o % (MC / 2)) * 2, kc = o / (MC / 2);
+        constexpr int HM = MP / 2, PH = MP / 2 + 1, HC = MC / 2;
+        // HOIST: a thread keeps its output column pair; everything that depends on the column only (mirror branch,
+        // column offsets, output column positions) leaves the loop
+        constexpr bool HOIST = (WST_OPT_HOIST_PROD || WST_OPT_PREFETCH) && NT % HC == 0;
+        constexpr bool PREF = WST_OPT_PREFETCH && HOIST;
+        // filter values of one output pair: alias (a, b) -> [pair member][orientation]
+        auto load_w = [&](const float* fb, float (&w)[F * F][2][GS]) {
+            static_for<0, F * F>([&](auto S) {
+                constexpr int sl = decltype(S)::value, a = sl / F, b = sl % F;
+                const float* fp = fb + ((size_t)a * MC * MP + b * MC) * GS;
+                if constexpr (GS == 2) {
+                    float4 t = *reinterpret_cast<const float4*>(fp);
+                    w[sl][0][0] = t.x; w[sl][0][1] = t.y; w[sl][1][0] = t.z; w[sl][1][1] = t.w;
+                } else {
+                    float2 t = *reinterpret_cast<const float2*>(fp);
+                    w[sl][0][0] = t.x; w[sl][1][0] = t.y;
+                }
+            });
+        };
+        float wn[F * F][2][GS];                       // PREF: the next pair's filter values, in flight during this pair
+        if constexpr (PREF) {
+            const int k0 = tid / HC;
+            load_w(filt + ((size_t)(k0 < MC ? k0 : 0) * MP + (tid % HC) * 2) * GS, wn);
+        }
+        for (int o = HOIST ? tid / HC : tid; o < (HOIST ? MC : MC * HC); o += (HOIST ? NT / HC : NT)) {
+            const int lc = HOIST ? (tid % HC) * 2 : (o % HC) * 2, kc = HOIST ? o : o / HC;
             float ar[2][GS], ai[2][GS];
             static_for<0, 2 * GS>([&](auto E) { ar[decltype(E)::value / GS][decltype(E)::value % GS] = 0.f;
                                                 ai[decltype(E)::value / GS][decltype(E)::value % GS] = 0.f; });
             float w[F * F][2][GS];
             cfloat u[F * F][2];
+            if constexpr (PREF) {
+                static_for<0, F * F * 2 * GS>([&](auto E) {
+                    constexpr int e = decltype(E)::value;
+                    w[e / (2 * GS)][(e / GS) % 2][e % GS] = wn[e / (2 * GS)][(e / GS) % 2][e % GS];
+                });
+                const int kn = kc + NT / HC;           // rows past the end re-read row kc (never used)
+                load_w(filt + ((size_t)(kn < MC ? kn : kc) * MP + lc) * GS, wn);
+            } else {
+                load_w(filt + ((size_t)kc * MP + lc) * GS, w);
+            }
             static_for<0, F>([&](auto A) {
                 constexpr int a = decltype(A)::value;
                 const int k = kc + a * MC;
@@ -832,14 +990,6 @@ WST_D void product_fold(int tid, const cfloat* uh, const float* filt, int rows, 
                 static_for<0, F>([&](auto B) {
                     constexpr int b = decltype(B)::value, sl = a * F + b;
                     const int l = lc + b * MC;                                      // even
-                    const float* fp = filt + ((size_t)k * MP + l) * GS;
-                    if constexpr (GS == 2) {
-                        float4 t = *reinterpret_cast<const float4*>(fp);
-                        w[sl][0][0] = t.x; w[sl][0][1] = t.y; w[sl][1][0] = t.z; w[sl][1][1] = t.w;
-                    } else {
-                        float2 t = *reinterpret_cast<const float2*>(fp);
-                        w[sl][0][0] = t.x; w[sl][1][0] = t.y;
-                    }
                     // U(k, l) and U(k, l+1) from the Hermitian half spectrum
                     if (l + 1 <= HM) { u[sl][0] = rd[l]; u[sl][1] = rd[l + 1]; }
                     else if (l >= HM + 1) { cfloat p = rm[MP - l], q = rm[MP - l - 1];
@@ -871,15 +1021,22 @@ WST_D void product_fold(int tid, const cfloat* uh, const float* filt, int rows, 
     } else if constexpr (!SPARSE) {
         // dense: all F*F aliases of U outputs per thread are loaded as one straight-line batch
         constexpr int U = cx_max(1, cx_min(8, 32 / (F * F * (GS + 2))));
-        for (int o0 = tid; o0 < MC * MC; o0 += NT * U) {
+        constexpr bool HOIST = WST_OPT_HOIST_PROD && NT % MC == 0;       // the thread's output column is fixed
+        for (int o0 = HOIST ? tid / MC : tid; o0 < (HOIST ? MC : MC * MC); o0 += (HOIST ? NT / MC : NT) * U) {
             float w[U][F * F][GS];
             cfloat u[U][F * F];
             int kc[U], lc[U];
             static_for<0, U>([&](auto Uc) {
                 constexpr int ui = decltype(Uc)::value;
-                int o = o0 + ui * NT;
-                o = o < MC * MC ? o : MC * MC - 1;          // tail items recompute the last output, never stored
-                lc[ui] = o % MC; kc[ui] = o / MC;
+                if constexpr (HOIST) {
+                    int k = o0 + ui * (NT / MC);
+                    kc[ui] = k < MC ? k : MC - 1;           // tail items recompute the last row, never stored
+                    lc[ui] = tid % MC;
+                } else {
+                    int o = o0 + ui * NT;
+                    o = o < MC * MC ? o : MC * MC - 1;      // tail items recompute the last output, never stored
+                    lc[ui] = o % MC; kc[ui] = o / MC;
+                }
                 static_for<0, F * F>([&](auto S) {
                     constexpr int sl = decltype(S)::value;
                     const int k = kc[ui] + (sl / F) * MC, l = lc[ui] + (sl % F) * MC;
@@ -899,7 +1056,7 @@ WST_D void product_fold(int tid, const cfloat* uh, const float* filt, int rows, 
                         ai[g] += u[ui][sl].y * w[ui][sl][g];
                     });
                 });
-                if (o0 + ui * NT < MC * MC) {
+                if (HOIST ? o0 + ui * (NT / MC) < MC : o0 + ui * NT < MC * MC) {
                     cfloat* op = out + Fft1<MC>::pi(kc[ui]) * PC + Fft1<MC>::pi(lc[ui]);
                     static_for<0, GS>([&](auto G) {
                         constexpr int g = decltype(G)::value;
@@ -910,8 +1067,9 @@ WST_D void product_fold(int tid, const cfloat* uh, const float* filt, int rows, 
         }
     } else {
         constexpr int NB = F >= 8 ? 4 : F;                // columns visited per row and batch
-        for (int o = tid; o < MC * MC; o += NT) {
-            int lc = o % MC, kc = o / MC;
+        constexpr bool HOIST = WST_OPT_HOIST_PROD && NT % MC == 0;       // fixed output column: its alias run leaves the loop
+        for (int o = HOIST ? tid / MC : tid; o < (HOIST ? MC : MC * MC); o += (HOIST ? NT / MC : NT)) {
+            const int lc = HOIST ? tid % MC : o % MC, kc = HOIST ? o : o / MC;
             float ar[GS], ai[GS];
             static_for<0, GS>([&](auto G) { ar[decltype(G)::value] = 0.f; ai[decltype(G)::value] = 0.f; });
             AliasRun ra = alias_run<MP, MC>(kc, rows), rb = alias_run<MP, MC>(lc, cols);
@@ -1235,6 +1393,67 @@ struct Cascade {
     cfloat* stage;       // shared tile of the staged passes (C::stage_cfloats(); global-workspace variant only)
     cfloat* u0h;         // per-CTA global scratch: N * (N/2+1)
     float* maps;         // this signal's output maps [K][HOUT][HOUT]
+    // input prefetch (TMA): raw H x W pixels of the next signal at sm + PF_OFF, completion on *mbar
+    // (the prefetch state lives in shared memory, not in registers that would stay live through the whole cascade:
+    // word 0-1 the mbarrier, word 2 its phase parity, word 3 "a prefetch is pending")
+    unsigned long long* mbar = nullptr;
+    // Small batches (the reference calls the extractor one image at a time, train_and_save_model.py:486-488): the
+    // first-order groups of a signal — a group of same-scale parents with all their children — are independent once
+    // U0^ exists, so `nparts` CTAs share one signal: every CTA runs the input stage, then takes the groups whose
+    // running index is congruent to `part`.  The last CTA to finish pools the signal (wst_cfg_inst.cu).
+    int part = 0, nparts = 1, unit = 0;
+    WST_D bool my_unit() { const int u = unit++; return nparts == 1 || u % nparts == part; }
+    // number of first-order groups of a plan with L orientations (host side: how far a signal can be split)
+    static WST_CX int num_units(int L) {
+        int n = 0;
+        for (int j = 0; j < J; ++j) n += (L + C::GP(j) - 1) / C::GP(j);
+        return n;
+    }
+    WST_D volatile unsigned* pf_state() const { return reinterpret_cast<volatile unsigned*>(mbar) + 2; }
+    // first cfloat of the raw-pixel area: right after the paired rows z0 of the input stage (16-byte aligned)
+    static constexpr int PF_OFF = ((N / 2) * (N + 1) + 1) & ~1;
+    static constexpr bool PF_COMPILED = WST_OPT_TMA && !C::WS_GLOBAL && C::CL == 1;
+    // the area is free while the last level runs if that level's arrays end below it
+    static constexpr bool PF_EARLY = C::level_total(J - 1, C::GP(J - 1)) <= PF_OFF;
+
+    // Can this signal's pixels be fetched by bulk copies?  float32 rows, 16-byte aligned, sizes in multiples of 16 bytes,
+    // and the raw area inside the data region.
+    WST_D bool pf_usable(const SignalSrc& x) const {
+        if (!PF_COMPILED || !x.f32 || x.stride != 1) return false;
+        const int H = pt.H, W = pt.W;
+        if (PF_OFF + (H * W + 1) / 2 > C::smem_cfloats()) return false;
+        if ((reinterpret_cast<size_t>(x.f32) & 15) != 0) return false;
+        return x.pitch == W ? (H * W) % 4 == 0 : (W % 4 == 0 && x.pitch % 4 == 0);
+    }
+
+    // Issue the bulk copies of signal x into the raw area (one phase; warp 0 issues, everybody passes the barrier).
+    WST_D void prefetch_input(const SignalSrc& x) {
+#ifdef __CUDA_ARCH__
+        if constexpr (PF_COMPILED) {
+            if (!pf_usable(x)) return;
+            ex.template phase<PK_INPUT * 8 + 1>([&](int tid) {
+                if (tid == 0) pf_state()[1] = 1u;
+                if (tid >= 32) return;
+                const int H = pt.H, W = pt.W;
+                float* raw = reinterpret_cast<float*>(sm + PF_OFF);
+                fence_proxy_async();                  // earlier generic-proxy writes to the area are ordered before the copies
+                if (tid == 0) mbar_expect_tx(mbar, (unsigned)(H * W * 4));
+                __syncwarp();
+                if (x.pitch == W) {                   // one contiguous patch: a few large copies
+                    const unsigned total = (unsigned)(H * W * 4), CH = 16384;
+                    for (unsigned o = tid * CH; o < total; o += 32 * CH)
+                        tma_bulk_g2s(reinterpret_cast<char*>(raw) + o, reinterpret_cast<const char*>(x.f32) + o,
+                                     total - o < CH ? total - o : CH, mbar);
+                } else {                              // a tile of a larger raster: one copy per row
+                    for (int r = tid; r < H; r += 32)
+                        tma_bulk_g2s(raw + r * W, x.f32 + (size_t)r * x.pitch, (unsigned)(W * 4), mbar);
+                }
+            });
+        }
+#else
+        (void)x;
+#endif
+    }
 
     WST_D const cfloat* tw(int j) const { return twsm + C::tw_offset(j); }
     WST_D const float* g(int j) const { return C::g_total == 0 ? pt.gr[j] : gsm + C::g_offset(j); }
@@ -1264,6 +1483,28 @@ struct Cascade {
     WST_D void input_stage(const SignalSrc& x) {
         constexpr int P = N + 1, HALF = N / 2, PH = N / 2 + 1;
         const int H = pt.H, W = pt.W, pt_top = pt.pad_top, pt_left = pt.pad_left;
+#ifdef __CUDA_ARCH__
+        if (PF_COMPILED && pf_state()[1]) {
+            // the pixels are (being) delivered to shared memory by the bulk copies issued during the previous signal
+            const float* raw = reinterpret_cast<const float*>(sm + PF_OFF);
+            const unsigned parity = pf_state()[0];
+            ex.template phase<PK_INPUT * 8>([&](int tid) {
+                mbar_wait(mbar, parity);
+                for (int o = tid; o < HALF * N; o += NT) {
+                    const int cs = o % N, rs = o / N;
+                    const int c = Fft1<N>::inv_pos_s(cs), r = Fft1<N>::inv_pos_s(rs);
+                    const int rp = r + HALF < N ? r + HALF : r + HALF - N;
+                    int sc = c - pt_left; sc = sc < 0 ? -sc : (sc >= W ? 2 * (W - 1) - sc : sc);
+                    int r0 = r - pt_top; r0 = r0 < 0 ? -r0 : (r0 >= H ? 2 * (H - 1) - r0 : r0);
+                    int r1 = rp - pt_top; r1 = r1 < 0 ? -r1 : (r1 >= H ? 2 * (H - 1) - r1 : r1);
+                    sm[rs * P + cs] = cmake(raw[r0 * W + sc], raw[r1 * W + sc]);
+                }
+            });
+            // (every thread has read the state before the barrier that closed the phase; the next write to it is in a
+            // later phase)
+            if (ex.base + (int)threadIdx.x == 0) { pf_state()[0] = parity ^ 1u; pf_state()[1] = 0u; }
+        } else
+#endif
         ex.template phase<PK_INPUT * 8>([&](int tid) {
             for (int o = tid; o < HALF * N; o += NT) {
                 const int cs = o % N, rs = o / N;                      // storage column / row (row < N/2)
@@ -1276,7 +1517,7 @@ struct Cascade {
             }
         });
         lowpass_maps<N, HOUT, HP, NT, 0, lp_banded(N, HOUT, 0) && !C::WS_GLOBAL>(ex, sm, 0, 1, g(0), g(0), pt.lpw[0], maps,
-                                                                              [](int) { return 0; });
+                                                                              [&](int) { return part == 0 ? 0 : -1; });
         cfloat* uh = sm + C::OFFB(0);
         rfft2_from_pairs<N, NT, 0, C::WS_GLOBAL, C::stage_cfloats()>(ex, sm, 0, uh, 1, tw(0), stage);
         ex.template phase<PK_U0_STORE * 8>([&](int tid) {
@@ -1307,6 +1548,7 @@ struct Cascade {
         const int L = pt.L;
         const int ngroups = (L + GPn - 1) / GPn;
         for (int grp = 0; grp < ngroups; ++grp) {
+            if (!my_unit()) continue;
             ex.template phase<PK_PROD1 * 8 + J1>([&](int tid) {
                 product_fold<N, M, GPn, NT>(tid, u0h, pt.psi1[J1] + (size_t)grp * N * N * GPn,
                                             pt.bb1[J1][grp][0], pt.bb1[J1][grp][1], sm);
@@ -1332,8 +1574,16 @@ struct Cascade {
     // Per-coefficient mean and population std over the h x w map (np.mean / np.std of
     // train_and_save_model.py:371-372), two-pass, from the maps this CTA has just written:
     //   feats[0][k] = mean, feats[1][k] = std.
+    // CG: the maps were written by other CTAs (split signals): read them through L2 (ld.global.cg), never from L1
+    template <bool CG = false>
     WST_D void pool(float* feats) {
         constexpr int NPIX = HOUT * HOUT;
+        auto ld4 = [](const float4* q) -> float4 {
+#ifdef __CUDA_ARCH__
+            if constexpr (CG) return __ldcg(q);
+#endif
+            return *q;
+        };
         const int K = pt.K;
         int parts = 1;
         while (parts < 8 && K * parts * 2 <= NT && NPIX / (parts * 2) >= 16) parts *= 2;
@@ -1343,7 +1593,7 @@ struct Cascade {
             for (int o = tid; o < K * parts; o += NT) {
                 const float4* p = reinterpret_cast<const float4*>(maps + (size_t)(o / parts) * NPIX + (o % parts) * slice);
                 float sacc = 0.f;
-                for (int i = 0; i < slice / 4; ++i) { float4 v = p[i]; sacc += (v.x + v.y) + (v.z + v.w); }
+                for (int i = 0; i < slice / 4; ++i) { float4 v = ld4(p + i); sacc += (v.x + v.y) + (v.z + v.w); }
                 scr[o] = sacc;
             }
         });
@@ -1356,7 +1606,7 @@ struct Cascade {
                 const float4* p = reinterpret_cast<const float4*>(maps + (size_t)k * NPIX + (o % parts) * slice);
                 float vacc = 0.f;
                 for (int i = 0; i < slice / 4; ++i) {
-                    float4 v = p[i];
+                    float4 v = ld4(p + i);
                     float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
                     vacc += (a * a + b * b) + (c * c + d * d);
                 }
@@ -1373,9 +1623,20 @@ struct Cascade {
         });
     }
 
-    WST_D void run(const SignalSrc& x, float* feats) {
+    // next: the signal this CTA will process after x (nullptr: none) — its pixels are prefetched while the last
+    // level of x runs (or right before pooling when the last level's arrays reach into the raw-pixel area)
+    WST_D void run(const SignalSrc& x, float* feats, const SignalSrc* next = nullptr) {
+        unit = 0;
         input_stage(x);
-        static_for<0, J>([&](auto Jc) { this->template level<decltype(Jc)::value>(); });
+        static_for<0, J>([&](auto Jc) {
+            constexpr int j = decltype(Jc)::value;
+            if constexpr (j == J - 1 && PF_EARLY) { if (next) prefetch_input(*next); }
+            this->template level<j>();
+        });
+        if constexpr (!PF_EARLY) {
+            // pooling keeps its partial sums at the start of the data region: 2 * K * parts floats
+            if (next && 8 * pt.K <= PF_OFF) prefetch_input(*next);
+        }
         if (feats) pool(feats);
     }
 };

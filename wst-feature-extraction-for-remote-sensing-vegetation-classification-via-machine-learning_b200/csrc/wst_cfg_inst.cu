@@ -23,10 +23,13 @@ typedef Cfg<WST_CFG_N, WST_CFG_J, WST_CFG_NT, (WST_CFG_GLOBAL != 0), WST_CFG_CL>
 template <class C, class Exec>
 __device__ __forceinline__ void run_cascade(Exec& ex, const PlanTables& pt, const InputDesc& in,
                                             long long nsig, cfloat* u0h_scratch, cfloat* workspace, float* maps_out,
-                                            float* maps_scratch, float* feats) {
+                                            float* maps_scratch, float* feats, int split = 1, int* done = nullptr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // slot = the CTA (or cluster of C::CL CTAs) that owns one signal at a time; its scratch areas are indexed by it
-    const int slot = blockIdx.x / C::CL, nslots = gridDim.x / C::CL;
+    // slot = the CTA (or cluster of C::CL CTAs) that owns one signal at a time; its scratch areas are indexed by it.
+    // split > 1 (small batches, shared-memory variant): `split` consecutive CTAs share the signals of one slot, each
+    // taking every split-th first-order group; U0^ scratch is then per CTA and the maps scratch per signal.
+    const int cta = blockIdx.x / C::CL;
+    const int slot = cta / split, nslots = (gridDim.x / C::CL) / split;
     cfloat* sbase = reinterpret_cast<cfloat*>(smem_raw);
     cfloat* sm = C::WS_GLOBAL ? workspace + (size_t)slot * C::workspace_cfloats() : sbase;
     cfloat* twsm = C::WS_GLOBAL ? sbase : sbase + C::smem_cfloats();
@@ -36,13 +39,34 @@ __device__ __forceinline__ void run_cascade(Exec& ex, const PlanTables& pt, cons
     cfloat* stage = reinterpret_cast<cfloat*>(gsm + C::g_total + (C::WS_GLOBAL ? 0 : C::lpbuf_floats()));
     const size_t map_elems = (size_t)pt.K * C::HOUT * C::HOUT;
     Cascade<C, Exec> prog{ex, pt, sm, twsm, gsm, lpbuf, stage,
-                          u0h_scratch + (size_t)slot * (C::N * (C::N / 2 + 1)), nullptr};
-    prog.load_twiddles();
+                          u0h_scratch + (size_t)cta * (C::N * (C::N / 2 + 1)), nullptr};
+    prog.part = cta % split; prog.nparts = split;
+    __shared__ int is_last;
+    __shared__ unsigned long long input_mbar[2];         // [0] completion barrier of the input prefetch (TMA bulk copies), [1] its state
+    if (threadIdx.x == 0) { mbar_init(&input_mbar[0], 1); input_mbar[1] = 0ull; }
+    prog.mbar = &input_mbar[0];
+    prog.load_twiddles();                                // its barrier also publishes the mbarrier initialisation
+    if (slot < nsig) prog.prefetch_input(signal_source(in, slot, pt.H, pt.W));
     for (long long s = slot; s < nsig; s += nslots) {
         // maps go to the caller's buffer, or to this slot's own (L2-resident) scratch when only features are wanted
-        prog.maps = maps_out ? maps_out + (size_t)s * map_elems : maps_scratch + (size_t)slot * map_elems;
+        prog.maps = maps_out ? maps_out + (size_t)s * map_elems
+                             : maps_scratch + (size_t)(split > 1 ? s : slot) * map_elems;
         const SignalSrc src = signal_source(in, s, pt.H, pt.W);
-        prog.run(src, feats ? feats + (size_t)s * 2 * pt.K : nullptr);
+        const bool has_next = s + nslots < nsig;
+        const SignalSrc nxt = signal_source(in, has_next ? s + nslots : s, pt.H, pt.W);
+        float* f = feats ? feats + (size_t)s * 2 * pt.K : nullptr;
+        if (split == 1) { prog.run(src, f, has_next ? &nxt : nullptr); continue; }
+        // shared signal: no pooling inside run(); the CTA that finishes last pools from the (L2) maps of all parts
+        prog.run(src, nullptr, has_next ? &nxt : nullptr);
+        if (!f) continue;
+        __threadfence();                                 // this thread's map stores are visible device-wide ...
+        __syncthreads();
+        if (threadIdx.x == 0) is_last = atomicAdd(&done[s], 1) == split - 1;     // ... before the CTA checks in
+        __syncthreads();
+        if (is_last) {
+            __threadfence();
+            prog.template pool<true>(f);
+        }
     }
 }
 
@@ -51,9 +75,9 @@ __device__ __forceinline__ void run_cascade(Exec& ex, const PlanTables& pt, cons
 template <class C>
 __global__ void __launch_bounds__(C::NTL, C::min_ctas())
 cascade_kernel(const __grid_constant__ PlanTables pt, const InputDesc in, long long nsig, cfloat* u0h_scratch,
-               cfloat* workspace, float* maps_out, float* maps_scratch, float* feats) {
+               cfloat* workspace, float* maps_out, float* maps_scratch, float* feats, int split, int* done) {
     DevExec<C::CL> ex{C::CL > 1 ? cluster_cta_rank() * C::NTL : 0};
-    run_cascade<C>(ex, pt, in, nsig, u0h_scratch, workspace, maps_out, maps_scratch, feats);
+    run_cascade<C>(ex, pt, in, nsig, u0h_scratch, workspace, maps_out, maps_scratch, feats, split, done);
 }
 
 // Debug twin: same program, executor that accumulates clock64() per phase tag; CTA 0's totals -> cycles.
@@ -88,8 +112,10 @@ cudaError_t launch_any(void (*kernel)(Args...), int slots, cudaStream_t st, Args
 
 template <class C>
 cudaError_t launch_cascade(const PlanTables& pt, const InputDesc& in, long long nsig, cfloat* u0h, cfloat* ws,
-                           float* maps_out, float* maps_scratch, float* feats, int slots, cudaStream_t st) {
-    return launch_any<C>(cascade_kernel<C>, slots, st, pt, in, nsig, u0h, ws, maps_out, maps_scratch, feats);
+                           float* maps_out, float* maps_scratch, float* feats, int slots, cudaStream_t st, int split,
+                           int* done) {
+    // slots = CTAs (clusters) in the grid; with split > 1 consecutive groups of `split` CTAs share their signals
+    return launch_any<C>(cascade_kernel<C>, slots, st, pt, in, nsig, u0h, ws, maps_out, maps_scratch, feats, split, done);
 }
 
 template <class C>
@@ -141,11 +167,13 @@ cudaError_t max_slots(int device, int* slots) {
 
 wst::CfgOps WST_CAT(wst_make_ops_, WST_CFG_N, _, WST_CFG_J)() {
     typedef ThisCfg C;
-    static_assert(C::smem_bytes() + kNumPhaseTags * 8 <= 232448,
+    static_assert(C::smem_bytes() + kNumPhaseTags * 8 + 16 <= 232448,
                   "configuration exceeds the 227 KB of shared memory a CTA may use");
     CfgOps o;
     o.N = C::N; o.J = C::J; o.NT = C::NT; o.hout = C::HOUT; o.cluster = C::CL;
     o.smem = C::smem_bytes();
+    o.can_split = !C::WS_GLOBAL && C::CL == 1;
+    o.num_units = &Cascade<C, HostExec<C::NT>>::num_units;
     o.workspace_cfloats = C::workspace_cfloats();
     o.kernel = (const void*)cascade_kernel<C>;
     o.build = &build_tables<C>;

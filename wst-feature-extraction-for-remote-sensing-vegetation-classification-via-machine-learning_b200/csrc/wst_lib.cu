@@ -114,7 +114,7 @@ const std::vector<CfgOps>& all_ops() {
     static const std::vector<CfgOps> ops = {
 #define CFG(n, j) wst_make_ops_##n##_##j(),
 #define CFGG(n, j) wst_make_ops_##n##_##j(),
-#include "wst_configs.inc"
+#include WST_CONFIGS_FILE
 #undef CFG
 #undef CFGG
     };
@@ -286,24 +286,40 @@ int forward_impl(const wst2d_plan* p, const InputDesc& in, long long nsig, float
     const size_t map_elems = (size_t)p->K * p->hout * p->wout;
     const size_t u0h_elems = (size_t)p->N * (p->N / 2 + 1);
     const size_t ws_elems = p->ops->workspace_cfloats;
-    const int grid = (int)(nsig < p->grid_max ? nsig : p->grid_max);
+    int grid = (int)(nsig < p->grid_max ? nsig : p->grid_max);
+    // small batch: share each signal among `split` CTAs (first-order groups are independent), up to one CTA per group
+    int split = 1;
+    if (p->ops->can_split && nsig * 2 <= p->grid_max && !getenv("WST_NO_SPLIT")) {
+        split = (int)(p->grid_max / nsig);
+        const int units = p->ops->num_units(p->L);
+        if (split > units) split = units;
+        if (split < 1) split = 1;
+        grid = (int)nsig * split;
+    }
     cfloat* d_u0h = own_u0h; float* d_maps = own_maps; cfloat* d_ws = own_ws;
+    int* d_done = nullptr;
     cudaError_t e = cudaSuccess;
     if (!d_u0h) e = pool_alloc(p, &d_u0h, (size_t)grid * u0h_elems * sizeof(cfloat), st);
     if (e == cudaSuccess && ws_elems && !d_ws) e = pool_alloc(p, &d_ws, (size_t)grid * ws_elems * sizeof(cfloat), st);
-    if (e == cudaSuccess && !maps_dev && !d_maps) e = pool_alloc(p, &d_maps, (size_t)grid * map_elems * sizeof(float), st);
+    if (e == cudaSuccess && !maps_dev && !d_maps)
+        e = pool_alloc(p, &d_maps, (size_t)(split > 1 ? nsig : grid) * map_elems * sizeof(float), st);
+    if (e == cudaSuccess && split > 1) {
+        e = pool_alloc(p, &d_done, (size_t)nsig * sizeof(int), st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_done, 0, (size_t)nsig * sizeof(int), st);
+    }
     int rc = WST2D_OK;
     if (e != cudaSuccess) {
         rc = fail(WST2D_ERR_CUDA, std::string("stream-ordered scratch allocation: ") + cudaGetErrorString(e));
     } else {
         prof_mark(p, p->prof_cascade, st);
-        e = p->ops->launch(p->pt, in, nsig, d_u0h, d_ws, maps_dev, maps_dev ? nullptr : d_maps, feats_dev, grid, st);
+        e = p->ops->launch(p->pt, in, nsig, d_u0h, d_ws, maps_dev, maps_dev ? nullptr : d_maps, feats_dev, grid, st, split, d_done);
         prof_mark(p, p->prof_cascade, st);
         if (e != cudaSuccess) rc = fail(WST2D_ERR_CUDA, std::string("cascade launch: ") + cudaGetErrorString(e));
     }
     if (!own_u0h && d_u0h) cudaFreeAsync(d_u0h, st);
     if (!own_ws && d_ws) cudaFreeAsync(d_ws, st);
     if (!own_maps && d_maps) cudaFreeAsync(d_maps, st);
+    if (d_done) cudaFreeAsync(d_done, st);
     return rc;
 }
 
@@ -467,7 +483,18 @@ int wst2d_forward_scene(const wst2d_plan* p, const float* raster_dev, int C, int
     return forward_impl(p, in, (long long)tile_count * C, feats_dev, maps_dev, (cudaStream_t)cuda_stream);
 }
 
+static int forward_host_impl(const wst2d_plan* p, const void* x_host, bool u8, int64_t B, int C, float* feats_host);
+
 int wst2d_forward_host(const wst2d_plan* p, const float* x_host, int64_t B, int C, float* feats_host) {
+    return forward_host_impl(p, x_host, false, B, C, feats_host);
+}
+
+int wst2d_forward_host_u8(const wst2d_plan* p, const uint8_t* x_host, int64_t B, int C, float* feats_host) {
+    return forward_host_impl(p, x_host, true, B, C, feats_host);
+}
+
+// x_host: float32 [B][C][H][W], or uint8 [B][H][W][C] (u8): the staging buffers hold either (sized for float32)
+static int forward_host_impl(const wst2d_plan* p, const void* x_host, bool u8, int64_t B, int C, float* feats_host) {
     if (!p) return fail(WST2D_ERR_ARG, "plan is NULL");
     if (B < 0 || C < 1) return fail(WST2D_ERR_ARG, "B must be >= 0 and C >= 1");
     if (B == 0) return WST2D_OK;
@@ -507,10 +534,11 @@ int wst2d_forward_host(const wst2d_plan* p, const float* x_host, int64_t B, int 
     for (long long s0 = 0; s0 < nsig && rc == WST2D_OK; s0 += chunk_sig, ++it) {
         long long n = nsig - s0 < chunk_sig ? nsig - s0 : chunk_sig;
         int i = it & 1;
-        cudaError_t e = cudaMemcpyAsync(hp.x[i], x_host + (size_t)s0 * sig_in, n * sig_in * sizeof(float),
+        const size_t esz = u8 ? 1 : sizeof(float);      // a chunk is a whole number of patches, so uint8 pixels stay HWC-aligned
+        cudaError_t e = cudaMemcpyAsync(hp.x[i], static_cast<const char*>(x_host) + (size_t)s0 * sig_in * esz, n * sig_in * esz,
                                         cudaMemcpyHostToDevice, hp.st[i]);
         if (e != cudaSuccess) { rc = fail(WST2D_ERR_CUDA, std::string("H2D: ") + cudaGetErrorString(e)); break; }
-        rc = forward_impl(p, plain_input(hp.x[i], 0), n, hp.f[i], nullptr, hp.st[i], hp.u0h[i], hp.maps[i], hp.ws[i]);
+        rc = forward_impl(p, plain_input(hp.x[i], u8 ? C : 0), n, hp.f[i], nullptr, hp.st[i], hp.u0h[i], hp.maps[i], hp.ws[i]);
         if (rc != WST2D_OK) break;
         e = cudaMemcpyAsync(feats_host + (size_t)s0 * sig_out, hp.f[i], n * sig_out * sizeof(float),
                             cudaMemcpyDeviceToHost, hp.st[i]);

@@ -17,16 +17,24 @@ struct CfgOps {
     const void* kernel;
     bool (*build)(int, const float*, const float*, std::vector<float>&, TableOffsets&, std::string&);
     void (*bind)(PlanTables&, const float*, const TableOffsets&);
-    // (tables, input descriptor, nsig, u0h scratch, workspace, maps_out | NULL, per-CTA maps scratch | NULL, feats | NULL, grid, stream)
-    cudaError_t (*launch)(const PlanTables&, const InputDesc&, long long, cfloat*, cfloat*, float*, float*, float*, int, cudaStream_t);
+    bool can_split;              // small batches: several CTAs may share one signal (shared-memory variant)
+    int (*num_units)(int L);     // first-order groups per signal = the largest useful split
+    // (tables, input descriptor, nsig, u0h scratch, workspace, maps_out | NULL, maps scratch | NULL, feats | NULL, grid, stream,
+    //  split = CTAs per signal, per-signal completion counters (split > 1))
+    cudaError_t (*launch)(const PlanTables&, const InputDesc&, long long, cfloat*, cfloat*, float*, float*, float*, int, cudaStream_t,
+                          int, int*);
     cudaError_t (*max_slots)(int device, int* slots);   // signals in flight (resident CTAs or clusters); also sets kernel attributes
     cudaError_t (*launch_prof)(const PlanTables&, const InputDesc&, long long, cfloat*, cfloat*, float*, float*, float*, long long*, int, cudaStream_t);
 };
 
 }  // namespace wst
 
+// the list of compiled cascades; tuning builds point WST_CONFIGS_FILE at a filtered copy
+#ifndef WST_CONFIGS_FILE
+#define WST_CONFIGS_FILE "wst_configs.inc"
+#endif
 #define CFG(n, j) wst::CfgOps wst_make_ops_##n##_##j();
 #define CFGG(n, j) wst::CfgOps wst_make_ops_##n##_##j();
-#include "wst_configs.inc"
+#include WST_CONFIGS_FILE
 #undef CFG
 #undef CFGG
