@@ -43,7 +43,7 @@ int run_cfg(int L, int max_order, int H, int W, const float* psi_hat, const floa
         Cascade<C, HostExec<C::NT>> prog{ex, pt, sm.data(), twsm.data(), gsm.data(), lpbuf.data(), stage.data(), u0h.data(), maps_out + s * map_sz};
         prog.load_twiddles();
         SignalSrc src{x + (size_t)s * H * W, nullptr, 1, W};
-        prog.run(src, feats_out ? feats_out + (size_t)s * 2 * pt.K : nullptr);
+        prog.run(src, [&]() -> float* { return feats_out ? feats_out + (size_t)s * 2 * pt.K : nullptr; });
     }
     return 0;
 }

@@ -1380,7 +1380,10 @@ WST_D void ifft2_modulus_lowpass(Exec& ex, cfloat* base, int narr, const cfloat*
 }
 
 // ------------------------------------------------------------------ the per-signal program
-template <class C, class Exec>
+// SPLIT: the signal is shared by several CTAs (small batches, see `part` below); a separate instantiation so that the
+// throughput kernel carries none of its state in registers — the 128 x 128 J=4 cascade sits exactly at its 96-register
+// budget and three more live values cost it 27 % in spills.
+template <class C, class Exec, bool SPLIT = false>
 struct Cascade {
     static constexpr int N = C::N, J = C::J, NT = C::NT, HOUT = C::HOUT, HP = C::HP;
 
@@ -1402,7 +1405,10 @@ struct Cascade {
     // U0^ exists, so `nparts` CTAs share one signal: every CTA runs the input stage, then takes the groups whose
     // running index is congruent to `part`.  The last CTA to finish pools the signal (wst_cfg_inst.cu).
     int part = 0, nparts = 1, unit = 0;
-    WST_D bool my_unit() { const int u = unit++; return nparts == 1 || u % nparts == part; }
+    WST_D bool my_unit() {
+        if constexpr (!SPLIT) return true;
+        else { const int u = unit++; return u % nparts == part; }
+    }
     // number of first-order groups of a plan with L orientations (host side: how far a signal can be split)
     static WST_CX int num_units(int L) {
         int n = 0;
@@ -1517,7 +1523,7 @@ struct Cascade {
             }
         });
         lowpass_maps<N, HOUT, HP, NT, 0, lp_banded(N, HOUT, 0) && !C::WS_GLOBAL>(ex, sm, 0, 1, g(0), g(0), pt.lpw[0], maps,
-                                                                              [&](int) { return part == 0 ? 0 : -1; });
+                                                                              [&](int) { return (!SPLIT || part == 0) ? 0 : -1; });
         cfloat* uh = sm + C::OFFB(0);
         rfft2_from_pairs<N, NT, 0, C::WS_GLOBAL, C::stage_cfloats()>(ex, sm, 0, uh, 1, tw(0), stage);
         ex.template phase<PK_U0_STORE * 8>([&](int tid) {
@@ -1623,21 +1629,27 @@ struct Cascade {
         });
     }
 
-    // next: the signal this CTA will process after x (nullptr: none) — its pixels are prefetched while the last
-    // level of x runs (or right before pooling when the last level's arrays reach into the raw-pixel area)
-    WST_D void run(const SignalSrc& x, float* feats, const SignalSrc* next = nullptr) {
-        unit = 0;
+    // next(SignalSrc&): fills in the signal this CTA will process after x and returns true, or returns false — its
+    // pixels are prefetched while the last level of x runs (or right before pooling when the last level's arrays reach
+    // into the raw-pixel area).  feats(): where the pooled features of x go (nullptr: no pooling here).  Both are
+    // callables evaluated where needed, so that nothing of them stays live in registers across the cascade.
+    struct NoNext { WST_D bool operator()(SignalSrc&) const { return false; } };
+    template <class FeatsFn, class NextFn = NoNext>
+    WST_D void run(const SignalSrc& x, FeatsFn feats, NextFn next = NextFn()) {
+        if constexpr (SPLIT) unit = 0;
         input_stage(x);
         static_for<0, J>([&](auto Jc) {
             constexpr int j = decltype(Jc)::value;
-            if constexpr (j == J - 1 && PF_EARLY) { if (next) prefetch_input(*next); }
+            if constexpr (j == J - 1 && PF_EARLY && PF_COMPILED) { SignalSrc nx; if (next(nx)) prefetch_input(nx); }
             this->template level<j>();
         });
-        if constexpr (!PF_EARLY) {
+        if constexpr (!PF_EARLY && PF_COMPILED) {
             // pooling keeps its partial sums at the start of the data region: 2 * K * parts floats
-            if (next && 8 * pt.K <= PF_OFF) prefetch_input(*next);
+            SignalSrc nx;
+            if (8 * pt.K <= PF_OFF && next(nx)) prefetch_input(nx);
         }
-        if (feats) pool(feats);
+        float* f = feats();
+        if (f) pool(f);
     }
 };
 

@@ -20,16 +20,16 @@ namespace {
 
 typedef Cfg<WST_CFG_N, WST_CFG_J, WST_CFG_NT, (WST_CFG_GLOBAL != 0), WST_CFG_CL> ThisCfg;
 
-template <class C, class Exec>
+template <class C, bool SPLIT, class Exec>
 __device__ __forceinline__ void run_cascade(Exec& ex, const PlanTables& pt, const InputDesc& in,
                                             long long nsig, cfloat* u0h_scratch, cfloat* workspace, float* maps_out,
                                             float* maps_scratch, float* feats, int split = 1, int* done = nullptr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // slot = the CTA (or cluster of C::CL CTAs) that owns one signal at a time; its scratch areas are indexed by it.
-    // split > 1 (small batches, shared-memory variant): `split` consecutive CTAs share the signals of one slot, each
+    // SPLIT (small batches, shared-memory variant): `split` consecutive CTAs share the signals of one slot, each
     // taking every split-th first-order group; U0^ scratch is then per CTA and the maps scratch per signal.
     const int cta = blockIdx.x / C::CL;
-    const int slot = cta / split, nslots = (gridDim.x / C::CL) / split;
+    const int slot = SPLIT ? cta / split : cta, nslots = SPLIT ? (gridDim.x / C::CL) / split : gridDim.x / C::CL;
     cfloat* sbase = reinterpret_cast<cfloat*>(smem_raw);
     cfloat* sm = C::WS_GLOBAL ? workspace + (size_t)slot * C::workspace_cfloats() : sbase;
     cfloat* twsm = C::WS_GLOBAL ? sbase : sbase + C::smem_cfloats();
@@ -38,9 +38,9 @@ __device__ __forceinline__ void run_cascade(Exec& ex, const PlanTables& pt, cons
     // tile of the staged FFT passes (global-workspace variant), after the tables; 8-byte aligned: all counts are even
     cfloat* stage = reinterpret_cast<cfloat*>(gsm + C::g_total + (C::WS_GLOBAL ? 0 : C::lpbuf_floats()));
     const size_t map_elems = (size_t)pt.K * C::HOUT * C::HOUT;
-    Cascade<C, Exec> prog{ex, pt, sm, twsm, gsm, lpbuf, stage,
-                          u0h_scratch + (size_t)cta * (C::N * (C::N / 2 + 1)), nullptr};
-    prog.part = cta % split; prog.nparts = split;
+    Cascade<C, Exec, SPLIT> prog{ex, pt, sm, twsm, gsm, lpbuf, stage,
+                                 u0h_scratch + (size_t)cta * (C::N * (C::N / 2 + 1)), nullptr};
+    if constexpr (SPLIT) { prog.part = cta % split; prog.nparts = split; }
     __shared__ int is_last;
     __shared__ unsigned long long input_mbar[2];         // [0] completion barrier of the input prefetch (TMA bulk copies), [1] its state
     if (threadIdx.x == 0) { mbar_init(&input_mbar[0], 1); input_mbar[1] = 0ull; }
@@ -50,22 +50,27 @@ __device__ __forceinline__ void run_cascade(Exec& ex, const PlanTables& pt, cons
     for (long long s = slot; s < nsig; s += nslots) {
         // maps go to the caller's buffer, or to this slot's own (L2-resident) scratch when only features are wanted
         prog.maps = maps_out ? maps_out + (size_t)s * map_elems
-                             : maps_scratch + (size_t)(split > 1 ? s : slot) * map_elems;
-        const SignalSrc src = signal_source(in, s, pt.H, pt.W);
-        const bool has_next = s + nslots < nsig;
-        const SignalSrc nxt = signal_source(in, has_next ? s + nslots : s, pt.H, pt.W);
-        float* f = feats ? feats + (size_t)s * 2 * pt.K : nullptr;
-        if (split == 1) { prog.run(src, f, has_next ? &nxt : nullptr); continue; }
-        // shared signal: no pooling inside run(); the CTA that finishes last pools from the (L2) maps of all parts
-        prog.run(src, nullptr, has_next ? &nxt : nullptr);
-        if (!f) continue;
-        __threadfence();                                 // this thread's map stores are visible device-wide ...
-        __syncthreads();
-        if (threadIdx.x == 0) is_last = atomicAdd(&done[s], 1) == split - 1;     // ... before the CTA checks in
-        __syncthreads();
-        if (is_last) {
-            __threadfence();
-            prog.template pool<true>(f);
+                             : maps_scratch + (size_t)(SPLIT ? s : slot) * map_elems;
+        auto next = [&](SignalSrc& o) -> bool {
+            if (s + nslots >= nsig) return false;
+            o = signal_source(in, s + nslots, pt.H, pt.W);
+            return true;
+        };
+        auto fptr = [&]() -> float* { return feats ? feats + (size_t)s * 2 * pt.K : nullptr; };
+        if constexpr (!SPLIT) {
+            prog.run(signal_source(in, s, pt.H, pt.W), fptr, next);
+        } else {
+            // shared signal: no pooling inside run(); the CTA that finishes last pools from the (L2) maps of all parts
+            prog.run(signal_source(in, s, pt.H, pt.W), []() -> float* { return nullptr; }, next);
+            if (!feats) continue;
+            __threadfence();                                 // this thread's map stores are visible device-wide ...
+            __syncthreads();
+            if (threadIdx.x == 0) is_last = atomicAdd(&done[s], 1) == split - 1;     // ... before the CTA checks in
+            __syncthreads();
+            if (is_last) {
+                __threadfence();
+                prog.template pool<true>(fptr());
+            }
         }
     }
 }
@@ -75,9 +80,20 @@ __device__ __forceinline__ void run_cascade(Exec& ex, const PlanTables& pt, cons
 template <class C>
 __global__ void __launch_bounds__(C::NTL, C::min_ctas())
 cascade_kernel(const __grid_constant__ PlanTables pt, const InputDesc in, long long nsig, cfloat* u0h_scratch,
-               cfloat* workspace, float* maps_out, float* maps_scratch, float* feats, int split, int* done) {
+               cfloat* workspace, float* maps_out, float* maps_scratch, float* feats) {
     DevExec<C::CL> ex{C::CL > 1 ? cluster_cta_rank() * C::NTL : 0};
-    run_cascade<C>(ex, pt, in, nsig, u0h_scratch, workspace, maps_out, maps_scratch, feats, split, done);
+    run_cascade<C, false>(ex, pt, in, nsig, u0h_scratch, workspace, maps_out, maps_scratch, feats);
+}
+
+// Small-batch twin (shared-memory variant only): `split` CTAs per signal, the last one to finish pools.
+template <class C>
+__global__ void __launch_bounds__(C::NTL, C::min_ctas())
+cascade_split_kernel(const __grid_constant__ PlanTables pt, const InputDesc in, long long nsig, cfloat* u0h_scratch,
+                     float* maps_out, float* maps_scratch, float* feats, int split, int* done) {
+    if constexpr (!C::WS_GLOBAL && C::CL == 1) {
+        DevExec<1> ex{0};
+        run_cascade<C, true>(ex, pt, in, nsig, u0h_scratch, nullptr, maps_out, maps_scratch, feats, split, done);
+    }
 }
 
 // Debug twin: same program, executor that accumulates clock64() per phase tag; CTA 0's totals -> cycles.
@@ -89,7 +105,7 @@ cascade_prof_kernel(const __grid_constant__ PlanTables pt, const InputDesc in, l
     for (int i = threadIdx.x; i < kNumPhaseTags; i += C::NTL) acc[i] = 0;
     __syncthreads();
     ProfExec<C::CL> ex{C::CL > 1 ? cluster_cta_rank() * C::NTL : 0, acc};
-    run_cascade<C>(ex, pt, in, nsig, u0h_scratch, workspace, maps_out, maps_scratch, feats);
+    run_cascade<C, false>(ex, pt, in, nsig, u0h_scratch, workspace, maps_out, maps_scratch, feats);
     if (blockIdx.x == 0)
         for (int i = threadIdx.x; i < kNumPhaseTags; i += C::NTL) cycles[i] = acc[i];
 }
@@ -115,7 +131,16 @@ cudaError_t launch_cascade(const PlanTables& pt, const InputDesc& in, long long 
                            float* maps_out, float* maps_scratch, float* feats, int slots, cudaStream_t st, int split,
                            int* done) {
     // slots = CTAs (clusters) in the grid; with split > 1 consecutive groups of `split` CTAs share their signals
-    return launch_any<C>(cascade_kernel<C>, slots, st, pt, in, nsig, u0h, ws, maps_out, maps_scratch, feats, split, done);
+    if (split > 1) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(cascade_split_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes());
+            if (e != cudaSuccess) return e;
+            attr_set = true;
+        }
+        return launch_any<C>(cascade_split_kernel<C>, slots, st, pt, in, nsig, u0h, maps_out, maps_scratch, feats, split, done);
+    }
+    return launch_any<C>(cascade_kernel<C>, slots, st, pt, in, nsig, u0h, ws, maps_out, maps_scratch, feats);
 }
 
 template <class C>
