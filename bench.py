@@ -36,6 +36,7 @@ CONFIGS = {   # name -> (M, J, L, max_order, C, default per-GPU batch)
     "repo": (128, 2, 8, 2, 3, 4096),
     "cfg4": (64, 3, 8, 2, 3, 8192),
     "cfg5": (512, 5, 8, 2, 4, 148),
+    "g100": (100, 2, 8, 2, 3, 2048),
     "p256j2": (256, 2, 8, 2, 3, 592),
     "p256j4": (256, 4, 8, 2, 3, 592),
 }
@@ -48,6 +49,8 @@ WORKLOAD_NAMES = {
             "each followed by Scattering2D J=3 L=8 max_order=2 from the uint8 pixels (BASELINE configs[3]); a step = the five "
             "models over the batch, patches/s counts every noised patch",
     "cfg5": "Scattering2D J=5 L=8 max_order=2, 512x512 4-band tiles (BASELINE configs[4]; global-workspace cascade)",
+    "g100": "Scattering2D J=2 L=8 max_order=2, 100x100 RGB patches (not a BASELINE shape: padded side 108 = 4*27 has no "
+            "compiled cascade, DFT-matrix engine)",
     "p256j2": "Scattering2D J=2 L=8 max_order=2, 256x256 RGB patches (not a BASELINE shape; global-workspace cascade)",
     "p256j4": "Scattering2D J=4 L=8 max_order=2, 256x256 RGB patches (not a BASELINE shape; global-workspace cascade)",
 }
