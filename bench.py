@@ -540,10 +540,11 @@ def run_ours(args, cfg):
             out["gather_verified"] = gather_verified
         if stream:
             out["stream"] = stream
-        try:
-            out["parity"] = parity_sample(plan, M, J, L, mo, C, dev)
-        except Exception as e:          # the bench line must not depend on the checker
-            out["parity"] = {"error": repr(e)}
+        if not args.no_parity:
+            try:
+                out["parity"] = parity_sample(plan, M, J, L, mo, C, dev)
+            except Exception as e:          # the bench line must not depend on the checker
+                out["parity"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(M, J, L, mo, C, sweep)
             if not args.no_latency:
@@ -565,6 +566,7 @@ def main():
     ap.add_argument("--no-gather", action="store_true", help="skip the NCCL feature all-gather at N>1")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-latency", action="store_true", help="skip the single-image latency probe")
+    ap.add_argument("--no-parity", action="store_true", help="skip the per-order parity sample against the oracle")
     ap.add_argument("--engine", default="auto", choices=["auto", "fft", "gemm", "gemm_tf32x3"],
                     help="fused FFT cascade (auto where compiled) or the DFT-matrix engine on the fp32 / tensor pipe")
     ap.add_argument("--stream-total", type=int, default=0,

@@ -163,6 +163,11 @@ WST_CX bool lp_banded(int m, int hout, int level) {
 #ifndef WST_OPT_TMA
 #define WST_OPT_TMA 1
 #endif
+//   WST_OPT_ROWSEQ  the fused last pass transforms its two rows one after the other (fewer live registers: what lets
+//                   the cascade run with 800 threads per CTA)
+#ifndef WST_OPT_ROWSEQ
+#define WST_OPT_ROWSEQ 0
+#endif
 #ifndef WST_STAGE_TC_MAX
 #define WST_STAGE_TC_MAX 16
 #endif
@@ -600,7 +605,7 @@ WST_D void pass_rows_final(int tid, cfloat* base, int narr, int AS, const float*
         cfloat* p0 = base + g * AS + x * P + i2;
         cfloat* p1 = p0 + POFF;
         cfloat a[NV];
-        if constexpr (NV > 16) {
+        if constexpr (NV > 16 || (WST_OPT_ROWSEQ && NV >= 8)) {
             // long butterflies (the 24-point lines of 576): one row at a time, so that only one butterfly's 2*NV
             // registers are live together with the NV moduli of the other
             float mc[NV];
