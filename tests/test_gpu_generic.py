@@ -101,3 +101,31 @@ def test_generic_engine_entry_points(wst):
     assert m1.shape == ref1.shape
     assert_parity(m1.reshape(15, p1.K, -1), ref1.reshape(15, p1.K, -1), J, L, max_order=1)
     assert plan.launch_count(5, 3) > 1
+
+
+def test_frontends_and_extractors_on_a_rectangular_image(wst):
+    """The reference's call pattern on an image whose shape has no compiled cascade: Scattering2D(J, L, shape=(H, W))
+    built from the image (train_and_save_model.py:355-359), numpy and torch frontends, training and inference layouts."""
+    import wst_b200.numpy, wst_b200.torch
+    from oracle import extract_wst_features_training, extract_wst_features_inference
+    H, W = 90, 120
+    rng = np.random.default_rng(4)
+    img = (rng.integers(0, 256, (3, H, W)) / 255.0).astype(np.float32)
+    S = wst_b200.numpy.Scattering2D(J=2, L=8, shape=(H, W))
+    out = S(img[0])
+    ref = oracle64(H, W, 2, 8)(img[0])
+    assert out.shape == ref.shape == (81, (wst.compute_padding(H, W, 2)[0] >> 2) - 2, (wst.compute_padding(H, W, 2)[1] >> 2) - 2)
+    assert out.dtype == np.float32
+    assert_parity(out[None].reshape(1, 81, -1), ref[None].reshape(1, 81, -1), 2, 8)
+    St = wst_b200.torch.Scattering2D(J=2, shape=(H, W), L=8)
+    with torch.no_grad():
+        t = St(torch.from_numpy(img[1]).unsqueeze(0).unsqueeze(0).contiguous())        # inference.py:250-254
+    assert tuple(t.shape) == (1, 1) + ref.shape
+    assert_parity(t[0].numpy().reshape(1, 81, -1), oracle64(H, W, 2, 8)(img[1])[None].reshape(1, 81, -1), 2, 8)
+    f_train = wst.extract_wst_features(img)
+    f_inf = wst.extract_wst_features_interleaved(img)
+    r_train = extract_wst_features_training(img, precision="double", cache_filters=True)
+    r_inf = extract_wst_features_inference(img.astype(np.float64), cache_filters=True)
+    assert f_train.shape == r_train.shape == (486,) and f_inf.shape == r_inf.shape == (486,)
+    assert_parity(f_train.reshape(3, 2, 81)[:, 0], r_train.reshape(3, 2, 81)[:, 0], 2, 8)
+    assert np.array_equal(np.ascontiguousarray(f_train.reshape(3, 2, 81).swapaxes(1, 2)).reshape(-1).astype(np.float64), f_inf)
