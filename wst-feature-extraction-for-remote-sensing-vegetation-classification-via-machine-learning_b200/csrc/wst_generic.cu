@@ -257,13 +257,15 @@ struct GenericPlan {
     size_t psi2[kMaxJ][kMaxJ];                      // [j2][j1]: scale j2 periodised to level j1: [L][Hj1][Wj1] real
     size_t floats_per_signal = 0;                   // workspace
     int sms = 148;
+    cudaMemPool_t pool = nullptr;                   // stream-ordered pool the workspace comes from (NULL: the device's default)
 };
 
 int generic_create(GenericPlan** out, int device, int H, int W, int J, int L, int max_order, int engine,
-                   const float* psi_hat, const float* phi_hat, std::string& err) {
+                   const float* psi_hat, const float* phi_hat, cudaMemPool_t pool, std::string& err) {
     const double kTwoPi = 6.283185307179586476925286766559;
     GenericPlan* p = new GenericPlan();
     p->device = device; p->H = H; p->W = W; p->J = J; p->L = L; p->max_order = max_order; p->engine = engine;
+    p->pool = pool;
     const int Hp = padded_size(H, J), Wp = padded_size(W, J);
     p->Hp = Hp; p->Wp = Wp; p->K = num_coefficients(J, L, max_order);
     p->h = (Hp >> J) - 2; p->w = (Wp >> J) - 2;
@@ -407,7 +409,10 @@ cudaError_t generic_forward(const GenericPlan* p, const InputDesc& in, long long
     const bool tc = p->engine == kEngineTf32x3, second = p->max_order >= 2;
     const long long CS = std::min<long long>(chunk_signals(p), nsig);
     float* ws = nullptr;
-    cudaError_t e = cudaMallocAsync(&ws, (size_t)CS * p->floats_per_signal * sizeof(float), st);
+    // from the plan's private pool: its blocks stay cached across synchronisations (the default pool gives memory back
+    // to the driver at every sync, which costs a 1.5 GB allocation per host-path call)
+    const size_t ws_bytes = (size_t)CS * p->floats_per_signal * sizeof(float);
+    cudaError_t e = p->pool ? cudaMallocFromPoolAsync((void**)&ws, ws_bytes, p->pool, st) : cudaMallocAsync(&ws, ws_bytes, st);
     if (e != cudaSuccess) { err = "cudaMallocAsync(generic workspace)"; return e; }
     const size_t HW = (size_t)Hp * Wp, LL = (size_t)L * L;
     auto al = [](size_t v) { return (v + 63) / 64 * 64; };

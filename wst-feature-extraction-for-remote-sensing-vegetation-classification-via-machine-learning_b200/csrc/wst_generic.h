@@ -29,7 +29,7 @@ struct GenericPlan;
 
 // psi_hat [J*L][Hp][Wp], phi_hat [Hp][Wp]: host copies of the full-resolution Fourier-domain filters.
 int generic_create(GenericPlan** out, int device, int H, int W, int J, int L, int max_order, int engine,
-                   const float* psi_hat, const float* phi_hat, std::string& err);
+                   const float* psi_hat, const float* phi_hat, cudaMemPool_t pool, std::string& err);
 void generic_destroy(GenericPlan* p);
 // feats [nsig][2][K] and/or maps [nsig][K][h][w] (either may be NULL).  Returns cudaSuccess or the failing call's error.
 cudaError_t generic_forward(const GenericPlan* p, const InputDesc& in, long long nsig, float* feats, float* maps,

@@ -378,7 +378,7 @@ int wst2d_plan_create_ex(wst2d_plan** out, int device, int H, int W, int J, int 
         std::string err;
         int grc = generic_create(&p->gen, device, H, W, J, L, max_order,
                                  p->engine == WST2D_ENGINE_GEMM_TF32X3 ? kEngineTf32x3 : kEngineSimt,
-                                 p->psi_hat.data(), p->phi_hat.data(), err);
+                                 p->psi_hat.data(), p->phi_hat.data(), p->pool, err);
         if (grc != 0) { delete p; return fail(grc == -2 ? WST2D_ERR_UNSUPPORTED : grc == -3 ? WST2D_ERR_CUDA : WST2D_ERR_ARG, err); }
         *out = p;
         return WST2D_OK;
