@@ -131,15 +131,8 @@ cudaError_t launch_cascade(const PlanTables& pt, const InputDesc& in, long long 
                            float* maps_out, float* maps_scratch, float* feats, int slots, cudaStream_t st, int split,
                            int* done) {
     // slots = CTAs (clusters) in the grid; with split > 1 consecutive groups of `split` CTAs share their signals
-    if (split > 1) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(cascade_split_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes());
-            if (e != cudaSuccess) return e;
-            attr_set = true;
-        }
+    if (split > 1)          // (its shared-memory attribute is set per device by max_slots at plan creation)
         return launch_any<C>(cascade_split_kernel<C>, slots, st, pt, in, nsig, u0h, maps_out, maps_scratch, feats, split, done);
-    }
     return launch_any<C>(cascade_kernel<C>, slots, st, pt, in, nsig, u0h, ws, maps_out, maps_scratch, feats);
 }
 
@@ -160,6 +153,10 @@ template <class C>
 cudaError_t max_slots(int device, int* slots) {
     cudaError_t e = cudaFuncSetAttribute(cascade_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes());
     if (e != cudaSuccess) return e;
+    if constexpr (!C::WS_GLOBAL && C::CL == 1) {        // function attributes are per device: set the split twin's here too
+        e = cudaFuncSetAttribute(cascade_split_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes());
+        if (e != cudaSuccess) return e;
+    }
     int sms = 0;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return e;
