@@ -59,6 +59,8 @@ enum { WST2D_ENGINE_AUTO = 0, WST2D_ENGINE_FFT = 1, WST2D_ENGINE_GEMM_SIMT = 2, 
 int wst2d_plan_create_ex(wst2d_plan** out, int device, int H, int W, int J, int L, int max_order, int engine);
 /* The engine a plan runs on (WST2D_ENGINE_FFT / _GEMM_SIMT / _GEMM_TF32X3). */
 int wst2d_plan_engine(const wst2d_plan* plan);
+/* Signals in flight of the fused cascade: CTAs of its persistent grid (SMs x resident CTAs per SM); 0 for the GEMM engines. */
+int wst2d_plan_grid(const wst2d_plan* plan);
 
 /* Geometry of a plan; any output pointer may be NULL. */
 int wst2d_query(const wst2d_plan* plan, int* K, int* h, int* w, int* Hp, int* Wp);

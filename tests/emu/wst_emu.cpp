@@ -32,7 +32,8 @@ int run_cfg(int L, int max_order, int H, int W, const float* psi_hat, const floa
     bind_tables<C>(pt, buf.data(), off);
     std::vector<cfloat> sm(C::smem_cfloats() + 64), twsm(C::tw_total);
     std::vector<float> gsm(C::g_total), lpbuf(C::lpbuf_floats() + 1);
-    std::vector<cfloat> stage(C::STAGE_BUFS * C::stage_cfloats() + 1);
+    // (the hybrid shared-memory region of the global-workspace variant aliases the stage tiles, as in the kernel)
+    std::vector<cfloat> stage(cx_max(C::STAGE_BUFS * C::stage_cfloats(), C::hybrid_cfloats()) + 1);
     std::vector<cfloat> u0h((size_t)C::N * (C::N / 2 + 1));
     HostExec<C::NT> ex;
     const size_t map_sz = (size_t)pt.K * C::HOUT * C::HOUT;

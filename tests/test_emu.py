@@ -153,3 +153,36 @@ def test_global_workspace_variant_vs_oracle(tmp_path):
         assert rc == 0
         assert not np.isnan(out).any() and floored_rel(out, ref) <= 1e-4 / 4, (M, J)
         assert floored_rel(feats[:, 0], ref.mean(axis=(-2, -1))) <= 1e-4 / 4
+
+
+def test_hybrid_global_workspace_variant_vs_oracle(tmp_path):
+    """Hybrid form of the global-workspace variant: level 0 in the workspace (staged passes), the levels that fit a small
+    shared-memory budget processed there like the shared-memory cascade, children of workspace-level parents included.
+    Replayed at small sides with budgets that put the split where the 256 x 256 / 512 x 512 builds have it."""
+    import ctypes
+    import subprocess
+    inc = tmp_path / "hyb_configs.inc"
+    inc.write_text("CFGG(160, 4)\nCFGG(80, 3)\nCFGG(48, 3)\n")
+    lib_path = tmp_path / "libwst_emu_hyb.so"
+    subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-DWST_GLOBAL_BUDGET=65536", "-DWST_HYBRID_BUDGET=7000",
+                    "-DWST_EMU_CONFIG_FILE=\"%s\"" % inc.name, "-I", str(tmp_path), "-I", emu.CSRC, "-I", emu.HERE,
+                    emu.HERE + "/wst_emu.cpp", "-o", str(lib_path)], check=True)
+    lib = ctypes.CDLL(str(lib_path))
+    lib.emu_forward.argtypes = [ctypes.c_int] * 6 + [ctypes.c_void_p] * 3 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    lib.emu_query.argtypes = [ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 3
+    for M, J, L, N in [(128, 4, 8, 160), (64, 3, 8, 80), (32, 3, 6, 48)]:
+        rng = np.random.default_rng(N + 1)
+        x = (rng.integers(0, 256, (1, M, M)) / 255.0).astype(np.float32)
+        S = Scattering2D(J=J, shape=(M, M), L=L, precision="double", cache_filters=True)
+        assert S._M_padded == N
+        psi = np.ascontiguousarray(np.stack([p["levels"][0] for p in S.psi]), np.float32)
+        phi = np.ascontiguousarray(S.phi["levels"][0], np.float32)
+        ref = S(x)
+        K, h = ref.shape[1], N // 2 ** J - 2
+        out = np.full((1, K, h, h), np.nan, np.float32)
+        feats = np.full((1, 2, K), np.nan, np.float32)
+        rc = lib.emu_forward(N, J, L, 2, M, M, psi.ctypes.data, phi.ctypes.data, x.ctypes.data, 1, out.ctypes.data,
+                             feats.ctypes.data)
+        assert rc == 0
+        assert not np.isnan(out).any() and floored_rel(out, ref) <= 1e-4 / 4, (M, J)
+        assert floored_rel(feats[:, 0], ref.mean(axis=(-2, -1))) <= 1e-4 / 4

@@ -82,6 +82,7 @@ class Plan:
                                             self.max_order, ENGINES[engine]))
         self._h = h
         self.engine = {v: k for k, v in ENGINES.items()}[lib.wst2d_plan_engine(h)]
+        self.grid = lib.wst2d_plan_grid(h)          # signals in flight of the fused cascade (persistent grid)
         q = [ctypes.c_int() for _ in range(5)]
         _lib.check(lib.wst2d_query(h, *[ctypes.byref(v) for v in q]))
         self.K, self.h, self.w, self.Hp, self.Wp = [v.value for v in q]

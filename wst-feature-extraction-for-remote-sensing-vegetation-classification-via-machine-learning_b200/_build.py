@@ -26,6 +26,8 @@ NVCC_FLAGS = _DEFS + ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=comput
 GLOBAL_VARIANT_THREADS = int(os.environ.get("WST_BUILD_NTL", 256))
 GLOBAL_VARIANT_CLUSTER = int(os.environ.get("WST_BUILD_CL", 1))
 GLOBAL_VARIANT_BUDGET = int(os.environ.get("WST_BUILD_BUDGET", 1 << 20))
+# Hybrid form: cfloats of shared memory in which the levels that fit are processed like the shared-memory cascade (0: none)
+GLOBAL_VARIANT_HYBRID = int(os.environ.get("WST_BUILD_HYBRID", 0))
 
 
 # Shared-memory configurations that run with other than the default 640 threads / 27000-cfloat data region:
@@ -35,6 +37,18 @@ SHARED_OVERRIDES = {(40, 2): (160, 6000), (80, 3): (320, 12000)}     # four / tw
 for _item in filter(None, os.environ.get("WST_BUILD_SHARED", "").split(",")):
     _n, _j, _t, _b = (int(v) for v in _item.split(":"))
     SHARED_OVERRIDES[(_n, _j)] = (_t, _b)
+
+
+# Global-workspace configurations built with other than GLOBAL_VARIANT_THREADS / no hybrid region:
+# {(N, J): (threads per CTA, hybrid shared-memory budget in cfloats)} — filled in from measurements
+GLOBAL_OVERRIDES = {
+    # 256 x 256: one 768-thread CTA per SM, levels <= 144^2 in a 216 KB shared-memory region (+26 / +45 / +37 % at J=2/3/4
+    # over two 256-thread CTAs with every level in the workspace)
+    (264, 2): (768, 27000), (272, 3): (768, 27000), (288, 4): (768, 27000),
+    # 512 x 512 J=5: two 256-thread CTAs per SM, levels <= 72^2 in a 100 KB region each (+4 %; one wide CTA loses 10-16 %
+    # on the 576^2 and 288^2 levels, which stay in the workspace)
+    (576, 5): (256, 12500),
+}
 
 
 def configs():
@@ -97,10 +111,12 @@ def build_library(force=False, verbose=False):
         o = os.path.join(OBJ, "wst_cfg_%d_%d.o" % (n, j))
         defs = ["-DWST_CFG_N=%d" % n, "-DWST_CFG_J=%d" % j]
         if glob:
-            cl, ntl, budget = GLOBAL_VARIANT_CLUSTER, GLOBAL_VARIANT_THREADS, GLOBAL_VARIANT_BUDGET
-            o = os.path.join(OBJ, "wst_cfg_%d_%d_cl%d_t%d_b%d.o" % (n, j, cl, ntl, budget))
+            cl, ntl, budget, hyb = GLOBAL_VARIANT_CLUSTER, GLOBAL_VARIANT_THREADS, GLOBAL_VARIANT_BUDGET, GLOBAL_VARIANT_HYBRID
+            if (n, j) in GLOBAL_OVERRIDES and "WST_BUILD_NTL" not in os.environ and "WST_BUILD_HYBRID" not in os.environ:
+                ntl, hyb = GLOBAL_OVERRIDES[(n, j)]
+            o = os.path.join(OBJ, "wst_cfg_%d_%d_cl%d_t%d_b%d_h%d.o" % (n, j, cl, ntl, budget, hyb))
             defs += ["-DWST_CFG_GLOBAL=1", "-DWST_CFG_NT=%d" % (ntl * cl), "-DWST_CFG_CL=%d" % cl,
-                     "-DWST_GLOBAL_BUDGET=%d" % budget]
+                     "-DWST_GLOBAL_BUDGET=%d" % budget, "-DWST_HYBRID_BUDGET=%d" % hyb]
         if (n, j) in SHARED_OVERRIDES:
             nt, budget = SHARED_OVERRIDES[(n, j)]
             o = os.path.join(OBJ, "wst_cfg_%d_%d_t%d_b%d.o" % (n, j, nt, budget))

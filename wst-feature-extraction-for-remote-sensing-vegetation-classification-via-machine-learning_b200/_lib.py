@@ -12,7 +12,7 @@ SYMBOLS = ["wst2d_plan_create", "wst2d_plan_destroy", "wst2d_query", "wst2d_forw
            "wst2d_version", "wst2d_profile", "wst2d_profile_read", "wst2d_fma_peak",
            "wst2d_debug_phase_cycles", "wst2d_forward_scene", "wst2d_advanced_stats",
            "wst2d_advanced_stats_last_error", "wst2d_add_noise", "wst2d_add_noise_draws", "wst2d_noise_last_error",
-           "wst2d_plan_create_ex", "wst2d_plan_engine", "wst2d_debug_num_phase_tags", "wst2d_forward_host_u8"]
+           "wst2d_plan_create_ex", "wst2d_plan_engine", "wst2d_debug_num_phase_tags", "wst2d_forward_host_u8", "wst2d_plan_grid"]
 
 _lib = None
 
@@ -30,6 +30,7 @@ def load():
     lib.wst2d_plan_create.argtypes = [ctypes.POINTER(vp), i32, i32, i32, i32, i32, i32]
     lib.wst2d_plan_create_ex.argtypes = [ctypes.POINTER(vp), i32, i32, i32, i32, i32, i32, i32]
     lib.wst2d_plan_engine.argtypes = [vp]
+    lib.wst2d_plan_grid.argtypes = [vp]
     lib.wst2d_debug_num_phase_tags.argtypes = []
     lib.wst2d_plan_destroy.argtypes = [vp]
     lib.wst2d_query.argtypes = [vp] + [ctypes.POINTER(i32)] * 5

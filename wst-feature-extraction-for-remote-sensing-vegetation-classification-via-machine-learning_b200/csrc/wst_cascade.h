@@ -55,6 +55,13 @@ constexpr int kSmemCfloats = WST_SMEM_BUDGET;   // data region budget: 216,000 B
 // together (GP, G2) and therefore the hot working set of one signal; the cluster variant picks it so that the working
 // sets of all signals in flight stay resident in L2.
 constexpr int kGlobalCfloats = WST_GLOBAL_BUDGET;
+// Hybrid form of the global-workspace variant: levels whose arrays (with their children) fit in this many cfloats of
+// shared memory are processed there, exactly like the shared-memory cascade; only the levels too large for one SM keep
+// their arrays in the workspace.  0: every level in the workspace.
+#ifndef WST_HYBRID_BUDGET
+#define WST_HYBRID_BUDGET 0
+#endif
+constexpr int kHybridCfloats = WST_HYBRID_BUDGET;
 
 // ------------------------------------------------------------------ 1-D factorisation n = R1*R2
 // Prime-factor (Good-Thomas) split n = P * Q with P the power-of-two part and Q the odd part: the two passes
@@ -206,13 +213,19 @@ struct Cfg {
         return 1;
     }
     static WST_CX bool has_children(int j) { return j < J - 1; }
-    static WST_CX int level_total(int j, int gp) {
+    // Memory space of a level's arrays.  Shared-memory cascade: everything in shared memory (budget kSmemCfloats).
+    // Global-workspace variant: the per-CTA workspace (budget kGlobalCfloats), except — hybrid form, SB > 0 — the levels
+    // that fit, with all their children, in SB cfloats of shared memory.  Children of a workspace-level parent that are
+    // themselves small enough also go to shared memory (their parent's spectrum is then read from the workspace).
+    static constexpr int SB = (WS_GLOBAL_ && CL_ == 1) ? kHybridCfloats : 0;
+    static WST_CX int level_total_in(int j, int gp, int budget, bool hybrid_parent) {
         int m = msize(j);
         if (!has_children(j)) return gp * vsz(m);
-        int room = BUDGET - gp * uhsz(m);
+        int room = budget - gp * uhsz(m);
         if (room < zend(m, gp)) return 1 << 30;
         int offb = zend(m, gp);
         for (int j2 = j + 1; j2 < J; ++j2) {
+            if (!hybrid_parent && WS_GLOBAL_ && SB > 0 && fits_shared(j2)) continue;   // those children live in shared memory
             int ch = pick_group(msize(j2), room) * vsz(msize(j2));
             if (ch > room) return 1 << 30;
             if (ch > offb) offb = ch;
@@ -220,25 +233,45 @@ struct Cfg {
         int t = offb + gp * uhsz(m);
         return t > gp * vsz(m) ? t : gp * vsz(m);
     }
+    static WST_CX bool fits_shared(int j) { return SB > 0 && level_total_in(j, 1, SB, true) <= SB; }
+    // true: level j's arrays are in shared memory
+    static WST_CX bool in_smem(int j) { return !WS_GLOBAL_ || (j > 0 && fits_shared(j)); }
+    static WST_CX int budget_of(int j) { return WS_GLOBAL_ ? (in_smem(j) ? SB : kGlobalCfloats) : kSmemCfloats; }
+    static WST_CX int level_total(int j, int gp) { return level_total_in(j, gp, budget_of(j), WS_GLOBAL_ && in_smem(j)); }
     // number of same-scale parents processed together at level j
     static WST_CX int GP(int j) {
-        for (int g = 8; g > 1; g /= 2) if (level_total(j, g) <= BUDGET) return g;
+        for (int g = 8; g > 1; g /= 2) if (level_total(j, g) <= budget_of(j)) return g;
         return 1;
     }
     static WST_CX int G2(int j1, int j2) {   // children group size
-        return pick_group(msize(j2), BUDGET - GP(j1) * uhsz(msize(j1)));
+        if (in_smem(j2) && !in_smem(j1)) return pick_group(msize(j2), SB);      // children alone in the shared region
+        return pick_group(msize(j2), budget_of(j1) - GP(j1) * uhsz(msize(j1)));
     }
     static WST_CX int OFFB(int j) {          // offset of the parents' half spectra
         int gp = GP(j), m = msize(j);
         int offb = zend(m, gp);
-        for (int j2 = j + 1; j2 < J; ++j2) offb = cx_max(offb, G2(j, j2) * vsz(msize(j2)));
+        for (int j2 = j + 1; j2 < J; ++j2)
+            if (in_smem(j2) == in_smem(j)) offb = cx_max(offb, G2(j, j2) * vsz(msize(j2)));
         return offb;
     }
+    // cfloats of the data region: shared memory (shared-memory cascade) or the per-CTA workspace (levels kept there)
     static WST_CX int smem_cfloats() {
         int t = 0;
-        for (int j = 0; j < J; ++j) t = cx_max(t, level_total(j, GP(j)));
+        for (int j = 0; j < J; ++j) if (!WS_GLOBAL_ || !in_smem(j)) t = cx_max(t, level_total(j, GP(j)));
         // input stage uses level-0 layout with one array
         t = cx_max(t, cx_max(vsz(N) / 2 + 1, OFFB(0) + uhsz(N)));
+        return t;
+    }
+    // cfloats of the hybrid shared-memory region (global-workspace variant): its levels, and the small children of
+    // workspace-level parents
+    static WST_CX int hybrid_cfloats() {
+        if (!WS_GLOBAL_ || SB == 0) return 0;
+        int t = 0;
+        for (int j = 1; j < J; ++j) {
+            if (!in_smem(j)) continue;
+            t = cx_max(t, level_total(j, GP(j)));
+            for (int j1 = 0; j1 < j; ++j1) if (!in_smem(j1)) t = cx_max(t, G2(j1, j) * vsz(msize(j)));
+        }
         return t;
     }
     static WST_CX int tw_offset(int j) {     // twiddle tables, one per level, appended after the data
@@ -271,7 +304,9 @@ struct Cfg {
     static WST_CX int lpbuf_floats() { return any_fused() ? LP_SLOTS * HOUT * HOUT : 0; }
     // bytes of dynamic shared memory, and of per-CTA global workspace (0 for the shared-memory variant)
     static WST_CX size_t smem_bytes() {
-        return (size_t)((WS_GLOBAL ? 0 : smem_cfloats()) + tw_total + STAGE_BUFS * stage_cfloats()) * sizeof(cfloat)
+        // (the hybrid region and the stage tiles share their shared memory: a staged pass and a shared-memory level
+        // never run at the same time)
+        return (size_t)((WS_GLOBAL ? 0 : smem_cfloats()) + tw_total + cx_max(STAGE_BUFS * stage_cfloats(), hybrid_cfloats())) * sizeof(cfloat)
                + (size_t)(g_total + (WS_GLOBAL ? 0 : lpbuf_floats())) * sizeof(float);
     }
     // Global-workspace variant: the passes of an inverse FFT run on shared-memory tiles (a batch of columns, then a
@@ -1466,6 +1501,10 @@ struct Cascade {
 #endif
     }
 
+    // data region of level Jl's arrays: the workspace / the shared-memory region, or — hybrid form of the
+    // global-workspace variant — the shared-memory region that aliases the stage tiles
+    template <int Jl> WST_D cfloat* base() const { return (C::WS_GLOBAL && C::in_smem(Jl)) ? stage : sm; }
+    template <int Jl> static WST_CX bool glob() { return C::WS_GLOBAL && !C::in_smem(Jl); }
     WST_D const cfloat* tw(int j) const { return twsm + C::tw_offset(j); }
     WST_D const float* g(int j) const { return C::g_total == 0 ? pt.gr[j] : gsm + C::g_offset(j); }
 
@@ -1542,13 +1581,14 @@ struct Cascade {
         const int L = pt.L;
         const int ngroups = (L + G - 1) / G;
         const int cbase = order2_base(J1, t1) + (J2 - J1 - 1) * L;
+        cfloat* arr = base<J2>();
         for (int grp = 0; grp < ngroups; ++grp) {
             ex.template phase<PK_PROD2 * 8 + J2>([&](int tid) {
                 product_fold<MP, MC, G, NT>(tid, uh_parent, pt.psi2[J2][J1] + (size_t)grp * MP * MP * G,
-                                            pt.bb2[pair_index(J2, J1)][grp][0], pt.bb2[pair_index(J2, J1)][grp][1], sm);
+                                            pt.bb2[pair_index(J2, J1)][grp][0], pt.bb2[pair_index(J2, J1)][grp][1], arr);
             });
-            ifft2_modulus_lowpass<MC, NT, J2, false, HOUT, HP, C::LP_SLOTS, C::WS_GLOBAL, C::stage_cfloats(), C::stage_rows(MC)>(
-                ex, sm, G, tw(J2), g(J2), pt.lpw[J2], lpbuf, maps, stage,
+            ifft2_modulus_lowpass<MC, NT, J2, false, HOUT, HP, C::LP_SLOTS, glob<J2>(), C::stage_cfloats(), C::stage_rows(MC)>(
+                ex, arr, G, tw(J2), g(J2), pt.lpw[J2], lpbuf, maps, stage,
                 [&](int a) { int t2 = grp * G + a; return t2 < L ? cbase + t2 : -1; });
         }
     }
@@ -1558,19 +1598,20 @@ struct Cascade {
         constexpr int M = C::msize(J1), GPn = C::GP(J1);
         const int L = pt.L;
         const int ngroups = (L + GPn - 1) / GPn;
+        cfloat* arr = base<J1>();
         for (int grp = 0; grp < ngroups; ++grp) {
             if (!my_unit()) continue;
             ex.template phase<PK_PROD1 * 8 + J1>([&](int tid) {
                 product_fold<N, M, GPn, NT>(tid, u0h, pt.psi1[J1] + (size_t)grp * N * N * GPn,
-                                            pt.bb1[J1][grp][0], pt.bb1[J1][grp][1], sm);
+                                            pt.bb1[J1][grp][0], pt.bb1[J1][grp][1], arr);
             });
-            ifft2_modulus_lowpass<M, NT, J1, C::has_children(J1), HOUT, HP, C::LP_SLOTS, C::WS_GLOBAL, C::stage_cfloats(), C::stage_rows(M)>(
-                ex, sm, GPn, tw(J1), g(J1), pt.lpw[J1], lpbuf, maps, stage,
+            ifft2_modulus_lowpass<M, NT, J1, C::has_children(J1), HOUT, HP, C::LP_SLOTS, glob<J1>(), C::stage_cfloats(), C::stage_rows(M)>(
+                ex, arr, GPn, tw(J1), g(J1), pt.lpw[J1], lpbuf, maps, stage,
                 [&](int a) { int t1 = grp * GPn + a; return t1 < L ? 1 + J1 * L + t1 : -1; });
             if constexpr (C::has_children(J1)) {
                 if (pt.max_order >= 2) {
-                    cfloat* uh = sm + C::OFFB(J1);
-                    rfft2_from_pairs<M, NT, J1, C::WS_GLOBAL, C::stage_cfloats()>(ex, sm, C::vsz(M), uh, GPn, tw(J1), stage);
+                    cfloat* uh = arr + C::OFFB(J1);
+                    rfft2_from_pairs<M, NT, J1, glob<J1>(), C::stage_cfloats()>(ex, arr, C::vsz(M), uh, GPn, tw(J1), stage);
                     for (int g = 0; g < GPn; ++g) {
                         int t1 = grp * GPn + g;
                         if (t1 >= L) break;

@@ -412,6 +412,11 @@ int wst2d_plan_create(wst2d_plan** out, int device, int H, int W, int J, int L, 
     return wst2d_plan_create_ex(out, device, H, W, J, L, max_order, WST2D_ENGINE_AUTO);
 }
 
+int wst2d_plan_grid(const wst2d_plan* p) {
+    if (!p) return fail(WST2D_ERR_ARG, "plan is NULL");
+    return p->grid_max;
+}
+
 int wst2d_plan_engine(const wst2d_plan* p) {
     if (!p) return fail(WST2D_ERR_ARG, "plan is NULL");
     return p->engine;
