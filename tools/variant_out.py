@@ -14,7 +14,8 @@ plan = wst_b200.get_plan(M, M, J, 8)
 rng = np.random.default_rng(5)
 x = torch.from_numpy((rng.integers(0, 256, (2, C, M, M)) / 255.0).astype(np.float32)).cuda()
 feats, maps = plan.forward(x, True, True)
-np.save("%s_%s.npy" % (prefix, name), maps.cpu().numpy())
+if not os.environ.get("WST_NO_SAVE"):
+    np.save("%s_%s.npy" % (prefix, name), maps.cpu().numpy())
 g = torch.Generator(device="cuda").manual_seed(1)
 xb = torch.randint(0, 256, (B, C, M, M), device="cuda", generator=g, dtype=torch.int32).float().div_(255.0)
 for _ in range(2):

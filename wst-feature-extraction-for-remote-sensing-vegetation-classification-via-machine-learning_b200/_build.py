@@ -40,14 +40,14 @@ for _item in filter(None, os.environ.get("WST_BUILD_SHARED", "").split(",")):
 
 
 # Global-workspace configurations built with other than GLOBAL_VARIANT_THREADS / no hybrid region:
-# {(N, J): (threads per CTA, hybrid shared-memory budget in cfloats)} — filled in from measurements
+# {(N, J): (threads per CTA, hybrid shared-memory budget in cfloats, workspace budget in cfloats)} — from measurements
 GLOBAL_OVERRIDES = {
-    # 256 x 256: one 768-thread CTA per SM, levels <= 144^2 in a 216 KB shared-memory region (+26 / +45 / +37 % at J=2/3/4
-    # over two 256-thread CTAs with every level in the workspace)
-    (264, 2): (768, 27000), (272, 3): (768, 27000), (288, 4): (768, 27000),
-    # 512 x 512 J=5: two 256-thread CTAs per SM, levels <= 72^2 in a 100 KB region each (+4 %; one wide CTA loses 10-16 %
-    # on the 576^2 and 288^2 levels, which stay in the workspace)
-    (576, 5): (256, 12500),
+    # 256 x 256: one 768-thread CTA per SM, levels <= 144^2 in a 216 KB shared-memory region, and a 1 MB workspace per CTA
+    # (one level-0 array at a time: the 148 workspaces stay in L2).  5.0 / 5.1 / 5.8 k -> 6.5 / 7.8 / 8.6 k patches/s at J=2/3/4.
+    (264, 2): (768, 27000, 1 << 17), (272, 3): (768, 27000, 1 << 17), (288, 4): (768, 27000, 1 << 17),
+    # 512 x 512 J=5: two 256-thread CTAs per SM, levels <= 72^2 in a 100 KB region each (+5 %; one wide CTA loses 10-16 %
+    # on the 576^2 and 288^2 levels, which stay in the workspace and do not fit L2 at any budget)
+    (576, 5): (256, 12500, 1 << 20),
 }
 
 
@@ -112,8 +112,8 @@ def build_library(force=False, verbose=False):
         defs = ["-DWST_CFG_N=%d" % n, "-DWST_CFG_J=%d" % j]
         if glob:
             cl, ntl, budget, hyb = GLOBAL_VARIANT_CLUSTER, GLOBAL_VARIANT_THREADS, GLOBAL_VARIANT_BUDGET, GLOBAL_VARIANT_HYBRID
-            if (n, j) in GLOBAL_OVERRIDES and "WST_BUILD_NTL" not in os.environ and "WST_BUILD_HYBRID" not in os.environ:
-                ntl, hyb = GLOBAL_OVERRIDES[(n, j)]
+            if (n, j) in GLOBAL_OVERRIDES and not any(k in os.environ for k in ("WST_BUILD_NTL", "WST_BUILD_HYBRID", "WST_BUILD_BUDGET")):
+                ntl, hyb, budget = GLOBAL_OVERRIDES[(n, j)]
             o = os.path.join(OBJ, "wst_cfg_%d_%d_cl%d_t%d_b%d_h%d.o" % (n, j, cl, ntl, budget, hyb))
             defs += ["-DWST_CFG_GLOBAL=1", "-DWST_CFG_NT=%d" % (ntl * cl), "-DWST_CFG_CL=%d" % cl,
                      "-DWST_GLOBAL_BUDGET=%d" % budget, "-DWST_HYBRID_BUDGET=%d" % hyb]

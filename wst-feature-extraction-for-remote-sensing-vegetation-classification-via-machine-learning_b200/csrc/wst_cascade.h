@@ -62,6 +62,9 @@ constexpr int kGlobalCfloats = WST_GLOBAL_BUDGET;
 #define WST_HYBRID_BUDGET 0
 #endif
 constexpr int kHybridCfloats = WST_HYBRID_BUDGET;
+#ifndef WST_GLOBAL_THREADS_PER_SM
+#define WST_GLOBAL_THREADS_PER_SM 512      // resident threads per SM the global-workspace variant is compiled for (register cap)
+#endif
 
 // ------------------------------------------------------------------ 1-D factorisation n = R1*R2
 // Prime-factor (Good-Thomas) split n = P * Q with P the power-of-two part and Q the odd part: the two passes
@@ -323,7 +326,7 @@ struct Cfg {
     // filled by another's work): bounded by shared memory and by keeping 640 threads' worth of registers per SM.
     static WST_CX int min_ctas() {
         if (CL > 1) return 1;
-        int by_smem = (int)(232448 / (smem_bytes() + 1024)), by_threads = (WS_GLOBAL ? 512 : 640) / NTL;
+        int by_smem = (int)(232448 / (smem_bytes() + 1024)), by_threads = (WS_GLOBAL ? WST_GLOBAL_THREADS_PER_SM : 640) / NTL;
         int m = by_smem < by_threads ? by_smem : by_threads;
         return m < 1 ? 1 : m;
     }
