@@ -39,6 +39,8 @@ CONFIGS = {   # name -> (M, J, L, max_order, C, default per-GPU batch)
     "g100": (100, 2, 8, 2, 3, 2048),
     "p256j2": (256, 2, 8, 2, 3, 592),
     "p256j4": (256, 4, 8, 2, 3, 592),
+    "p256j5": (256, 5, 8, 2, 3, 592),
+    "p96j2": (96, 2, 8, 2, 3, 8192),
 }
 WORKLOAD_NAMES = {
     "cfg1": "Scattering2D J=2 L=8 max_order=2, 32x32 RGB patches (BASELINE configs[0])",
@@ -53,6 +55,8 @@ WORKLOAD_NAMES = {
             "compiled cascade, DFT-matrix engine)",
     "p256j2": "Scattering2D J=2 L=8 max_order=2, 256x256 RGB patches (not a BASELINE shape; global-workspace cascade)",
     "p256j4": "Scattering2D J=4 L=8 max_order=2, 256x256 RGB patches (not a BASELINE shape; global-workspace cascade)",
+    "p256j5": "Scattering2D J=5 L=8 max_order=2, 256x256 RGB patches (not a BASELINE shape; hybrid global-workspace cascade)",
+    "p96j2": "Scattering2D J=2 L=8 max_order=2, 96x96 RGB patches (not a BASELINE shape; shared-memory cascade, padded side 104 = 8*13)",
 }
 
 

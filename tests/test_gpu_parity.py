@@ -20,7 +20,8 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 CONFIGS = [(32, 2, 8), (64, 3, 8), (128, 4, 8), (128, 2, 8), (32, 3, 6),
-           (32, 1, 8), (64, 2, 8), (128, 3, 8), (32, 4, 8), (64, 4, 8)]
+           (32, 1, 8), (64, 2, 8), (128, 3, 8), (32, 4, 8), (64, 4, 8),
+           (48, 3, 8), (96, 2, 8), (96, 4, 8)]
 
 
 def floored_rel(a, b):
@@ -152,13 +153,14 @@ def test_cfg5_512_J5_multispectral(wst):
     assert torch.equal(f1[0, 0], feats[0, 3])
 
 
-@pytest.mark.parametrize("J,N,h", [(2, 264, 64), (3, 272, 32), (4, 288, 16)])
+@pytest.mark.parametrize("J,N,h", [(2, 264, 64), (3, 272, 32), (4, 288, 16), (5, 320, 8)])
 def test_256x256_patches(wst, J, N, h):
-    """256x256 patches (padded sides 264 = 22*12, 272 = 16*17, 288 = 16*18) run through the global-workspace cascade."""
+    """256x256 patches (padded sides 264 = 22*12, 272 = 16*17, 288 = 16*18, 320 = 16*20) run through the global-workspace
+    cascade in its hybrid form: level 0 in the workspace, the levels that fit one SM in shared memory."""
     rng = np.random.default_rng(100 + J)
     x = (rng.integers(0, 256, (3, 1, 256, 256)) / 255.0).astype(np.float32)
     plan = wst.get_plan(256, 256, J, 8)
-    assert (plan.h, plan.Hp) == (h, N)
+    assert (plan.h, plan.Hp, plan.engine) == (h, N, "fft")
     feats, maps = plan.forward(torch.from_numpy(x).cuda(), True, True)
     ref = oracle64(256, J, 8)(x[:2, 0])
     assert floored_rel(maps[:2, 0].cpu().numpy().reshape(2, -1), ref.reshape(2, -1)) <= TOL

@@ -1641,8 +1641,8 @@ struct Cascade {
         };
         const int K = pt.K;
         int parts = 1;
-        while (parts < 8 && K * parts * 2 <= NT && NPIX / (parts * 2) >= 16) parts *= 2;
-        const int slice = NPIX / parts;                      // NPIX is a multiple of 4, parts a power of two <= 8
+        while (parts < 8 && K * parts * 2 <= NT && NPIX / (parts * 2) >= 16 && NPIX % (parts * 8) == 0) parts *= 2;
+        const int slice = NPIX / parts;                      // a multiple of 4 (the slices are read as float4)
         float* scr = reinterpret_cast<float*>(sm);           // the data region is free at the end of a signal
         ex.template phase<PK_POOL * 8>([&](int tid) {
             for (int o = tid; o < K * parts; o += NT) {
