@@ -432,6 +432,9 @@ int wst2d_plan_destroy(wst2d_plan* plan) {
     }
     cudaFree(plan->d_tables);
     generic_destroy(plan->gen);
+    // give the scratch this plan's forward calls left cached in the device's private pool back to the driver (other plans
+    // of the device re-grow it on their next call)
+    if (plan->pool) { cudaDeviceSynchronize(); cudaMemPoolTrimTo(plan->pool, 0); }
     delete plan;
     return WST2D_OK;
 }
