@@ -50,7 +50,8 @@ WORKLOAD_NAMES = {
     "cfg4": "noise-robustness sweep: gaussian / salt_and_pepper / speckle / poisson / uniform noise on uint8 64x64 RGB patches, "
             "each followed by Scattering2D J=3 L=8 max_order=2 from the uint8 pixels (BASELINE configs[3]); a step = the five "
             "models over the batch, patches/s counts every noised patch",
-    "cfg5": "Scattering2D J=5 L=8 max_order=2, 512x512 4-band tiles (BASELINE configs[4]; global-workspace cascade)",
+    "cfg5": "whole-scene tiling: Scattering2D J=5 L=8 max_order=2 over the 512x512 tiles of a 4-band raster, tiles read in place "
+            "by the cascade's input stage (BASELINE configs[4]; hybrid global-workspace cascade), tiles/s",
     "g100": "Scattering2D J=2 L=8 max_order=2, 100x100 RGB patches (not a BASELINE shape: padded side 108 = 4*27 has no "
             "compiled cascade, DFT-matrix engine)",
     "p256j2": "Scattering2D J=2 L=8 max_order=2, 256x256 RGB patches (not a BASELINE shape; global-workspace cascade)",
@@ -222,7 +223,7 @@ def latency_probe(dev):
     return {"call": "extract_wst_features(img[3,128,128]) J=2 L=8, host in / host out, plan cached",
             "ms_per_image": round(split, 4), "ms_per_image_one_cta_per_signal": round(single, 4),
             "cpu_as_called_ms": round(cpu_as_called, 1),
-            "note": "3 signals: first-order groups split over CTAs (last CTA pools); CPU = oracle as the reference calls it "
+            "note": "3 signals: units of (first-order group, child group) split over CTAs, the last CTA pools; CPU = oracle as the reference calls it "
                     "(filter bank rebuilt per image, train_and_save_model.py:359)"}
 
 
@@ -328,12 +329,18 @@ def run_ours(args, cfg):
     F = C * 2 * K
     plan = wst_b200.get_plan(M, M, J, L, mo, dev, engine=args.engine)
     sweep = args.config == "cfg4"
+    scene = args.config == "cfg5"            # whole-scene tiling: the tiles are read straight from a [C, Himg, Wimg] raster
+    nx_tiles = 16
+    ny_tiles = (B + nx_tiles - 1) // nx_tiles
 
     def make_input(r):
-        """The synthetic batch of rank r (seed 42 + 1000 r): uint8 HWC pixels for the noise sweep, k/255 float32 CHW else."""
+        """The synthetic batch of rank r (seed 42 + 1000 r): uint8 HWC pixels for the noise sweep, a multispectral raster of
+        ny x 16 tiles for the scene tiler, k/255 float32 CHW patches else."""
         gen = torch.Generator(device=dev).manual_seed(42 + 1000 * r)
         if sweep:
             return torch.randint(0, 256, (B, M, M, C), device=dev, generator=gen, dtype=torch.int32).to(torch.uint8)
+        if scene:
+            return torch.randint(0, 256, (C, ny_tiles * M, nx_tiles * M), device=dev, generator=gen, dtype=torch.int32).float().div_(255.0)
         return torch.randint(0, 256, (B, C, M, M), device=dev, generator=gen, dtype=torch.int32).float().div_(255.0)
 
     x = make_input(rank)
@@ -343,6 +350,8 @@ def run_ours(args, cfg):
     pending = []                                           # (work, gathered matrix) of gathers still in flight
 
     def compute():
+        if scene:
+            return plan.forward_scene(x, tile_range=(0, B))[0].view(B, F)
         if not sweep:
             return plan.forward(x)[0].view(B, F)
         outs = [plan.forward(wst_b200.add_noise(x, m, i, seed=42))[0].view(B, F) for m, i in NOISE]
@@ -406,6 +415,8 @@ def run_ours(args, cfg):
             xr = make_input(r)
             if sweep:
                 fr = plan.forward(wst_b200.add_noise(xr, NOISE[0][0], NOISE[0][1], seed=42)[:nchk].contiguous())[0].view(nchk, F)
+            elif scene:
+                fr = plan.forward_scene(xr, tile_range=(0, nchk))[0].view(nchk, F)
             else:
                 fr = plan.forward(xr[:nchk].contiguous())[0].view(nchk, F)
             ok = ok and bool(torch.equal(gathered[r * rows:r * rows + nchk], fr))
@@ -429,6 +440,17 @@ def run_ours(args, cfg):
             torch.cuda.synchronize()
         h2d, d2h = B * M * M * C, len(NOISE) * B * F * 4
         api = "torch H2D of the clean uint8 batch, wst_b200.add_noise + Plan.forward(uint8) per model, D2H of the features"
+    elif scene:
+        xh = torch.empty(tuple(x.shape), dtype=torch.float32).pin_memory()
+        xh.copy_(x)
+        fh = torch.empty((B, C, 2, K), dtype=torch.float32).pin_memory()
+
+        def e2e_step():       # the raster from pinned host memory, tiled on the device, per-tile features back to the host
+            f = plan.forward_scene(xh.to(dev, non_blocking=True), tile_range=(0, B))[0]
+            fh.copy_(f, non_blocking=True)
+            torch.cuda.synchronize()
+        h2d, d2h = x.numel() * 4, B * F * 4
+        api = "torch H2D of the [C, Himg, Wimg] raster, Plan.forward_scene (wst2d_forward_scene: tiles read in place), D2H of the features"
     else:
         xh = torch.empty((B, C, M, M), dtype=torch.float32).pin_memory()
         xh.copy_(x)

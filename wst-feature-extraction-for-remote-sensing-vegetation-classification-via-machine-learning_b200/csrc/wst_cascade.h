@@ -1447,16 +1447,33 @@ struct Cascade {
     // first-order groups of a signal — a group of same-scale parents with all their children — are independent once
     // U0^ exists, so `nparts` CTAs share one signal: every CTA runs the input stage, then takes the groups whose
     // running index is congruent to `part`.  The last CTA to finish pools the signal (wst_cfg_inst.cu).
+    // A unit of shared work is (first-order group, one group of its children): every CTA that owns a unit of a group
+    // rebuilds that group's parents (product, inverse FFT, forward FFT), the owner of the group's first unit also
+    // writes the parents' own maps, and each CTA transforms only its child groups.  Groups without children are one unit.
     int part = 0, nparts = 1, unit = 0;
-    WST_D bool my_unit() {
-        if constexpr (!SPLIT) return true;
-        else { const int u = unit++; return u % nparts == part; }
-    }
-    // number of first-order groups of a plan with L orientations (host side: how far a signal can be split)
-    static WST_CX int num_units(int L) {
+    // child groups of one first-order group at level j (all its parents, all deeper scales)
+    static WST_CX int child_tasks(int j, int L) {
+        if (!C::has_children(j)) return 1;
         int n = 0;
-        for (int j = 0; j < J; ++j) n += (L + C::GP(j) - 1) / C::GP(j);
+        for (int j2 = j + 1; j2 < J; ++j2) n += (L + C::G2(j, j2) - 1) / C::G2(j, j2);
+        return n * C::GP(j);
+    }
+    // number of units of a plan with L orientations and max_order (host side: how far a signal can be split)
+    static WST_CX int num_units(int L, int max_order = 2) {
+        int n = 0;
+        for (int j = 0; j < J; ++j) n += ((L + C::GP(j) - 1) / C::GP(j)) * (max_order >= 2 ? child_tasks(j, L) : 1);
         return n;
+    }
+    // does unit u belong to this CTA?
+    WST_D bool mine(int u) const { return !SPLIT || u % nparts == part; }
+    // does any unit of [first, first + n) belong to this CTA?
+    WST_D bool any_mine(int first, int n) const {
+        if constexpr (!SPLIT) return true;
+        else {
+            if (n >= nparts) return true;
+            const int r = first % nparts, d = part >= r ? part - r : part + nparts - r;
+            return d < n;
+        }
     }
     WST_D volatile unsigned* pf_state() const { return reinterpret_cast<volatile unsigned*>(mbar) + 2; }
     // first cfloat of the raw-pixel area: right after the paired rows z0 of the input stage (16-byte aligned)
@@ -1578,14 +1595,16 @@ struct Cascade {
         });
     }
 
+    // ubase: index of the first unit of this parent's child groups at scale J2 (SPLIT: only the groups this CTA owns run)
     template <int J1, int J2>
-    WST_D void children(const cfloat* uh_parent, int t1) {
+    WST_D void children(const cfloat* uh_parent, int t1, int ubase) {
         constexpr int MP = C::msize(J1), MC = C::msize(J2), G = C::G2(J1, J2);
         const int L = pt.L;
         const int ngroups = (L + G - 1) / G;
         const int cbase = order2_base(J1, t1) + (J2 - J1 - 1) * L;
         cfloat* arr = base<J2>();
         for (int grp = 0; grp < ngroups; ++grp) {
+            if (!mine(ubase + grp)) continue;
             ex.template phase<PK_PROD2 * 8 + J2>([&](int tid) {
                 product_fold<MP, MC, G, NT>(tid, uh_parent, pt.psi2[J2][J1] + (size_t)grp * MP * MP * G,
                                             pt.bb2[pair_index(J2, J1)][grp][0], pt.bb2[pair_index(J2, J1)][grp][1], arr);
@@ -1601,25 +1620,33 @@ struct Cascade {
         constexpr int M = C::msize(J1), GPn = C::GP(J1);
         const int L = pt.L;
         const int ngroups = (L + GPn - 1) / GPn;
+        const bool second = C::has_children(J1) && pt.max_order >= 2;
+        const int ntasks = second ? child_tasks(J1, L) : 1;          // units of one group
         cfloat* arr = base<J1>();
         for (int grp = 0; grp < ngroups; ++grp) {
-            if (!my_unit()) continue;
+            int first = 0;
+            if constexpr (SPLIT) { first = unit; unit += ntasks; if (!any_mine(first, ntasks)) continue; }
+            const bool own_maps = mine(first);                        // the owner of the group's first unit writes S1
             ex.template phase<PK_PROD1 * 8 + J1>([&](int tid) {
                 product_fold<N, M, GPn, NT>(tid, u0h, pt.psi1[J1] + (size_t)grp * N * N * GPn,
                                             pt.bb1[J1][grp][0], pt.bb1[J1][grp][1], arr);
             });
             ifft2_modulus_lowpass<M, NT, J1, C::has_children(J1), HOUT, HP, C::LP_SLOTS, glob<J1>(), C::stage_cfloats(), C::stage_rows(M)>(
                 ex, arr, GPn, tw(J1), g(J1), pt.lpw[J1], lpbuf, maps, stage,
-                [&](int a) { int t1 = grp * GPn + a; return t1 < L ? 1 + J1 * L + t1 : -1; });
+                [&](int a) { int t1 = grp * GPn + a; return (t1 < L && own_maps) ? 1 + J1 * L + t1 : -1; });
             if constexpr (C::has_children(J1)) {
                 if (pt.max_order >= 2) {
                     cfloat* uh = arr + C::OFFB(J1);
                     rfft2_from_pairs<M, NT, J1, glob<J1>(), C::stage_cfloats()>(ex, arr, C::vsz(M), uh, GPn, tw(J1), stage);
+                    int ubase = first;
                     for (int g = 0; g < GPn; ++g) {
                         int t1 = grp * GPn + g;
-                        if (t1 >= L) break;
                         const cfloat* uhp = uh + g * C::uhsz(M);
-                        static_for<J1 + 1, J>([&](auto J2c) { this->template children<J1, decltype(J2c)::value>(uhp, t1); });
+                        static_for<J1 + 1, J>([&](auto J2c) {
+                            constexpr int j2 = decltype(J2c)::value;
+                            if (t1 < L) this->template children<J1, j2>(uhp, t1, ubase);
+                            ubase += (L + C::G2(J1, j2) - 1) / C::G2(J1, j2);
+                        });
                     }
                 }
             }

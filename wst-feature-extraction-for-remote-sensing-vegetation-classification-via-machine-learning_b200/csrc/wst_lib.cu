@@ -291,7 +291,7 @@ int forward_impl(const wst2d_plan* p, const InputDesc& in, long long nsig, float
     int split = 1;
     if (p->ops->can_split && nsig * 2 <= p->grid_max && !getenv("WST_NO_SPLIT")) {
         split = (int)(p->grid_max / nsig);
-        const int units = p->ops->num_units(p->L);
+        const int units = p->ops->num_units(p->L, p->max_order);
         if (split > units) split = units;
         if (split < 1) split = 1;
         grid = (int)nsig * split;
