@@ -49,8 +49,9 @@ int wst2d_plan_destroy(wst2d_plan* plan);
 /* Same with an explicit engine.  The reference builds its transform from whatever image it loads
  * (train_and_save_model.py:355-359), so every (H, W) with 2^J <= min(H, W), rectangular included, and every L is
  * accepted:
- *   WST2D_ENGINE_AUTO        the fused shared-memory FFT cascade when one is compiled for the padded size (square
- *                            sides 36..160, 264..288, 576 with L <= 8), otherwise WST2D_ENGINE_GEMM_SIMT
+ *   WST2D_ENGINE_AUTO        the fused FFT cascade when one is compiled for the padded size (square images of side 32,
+ *                            48, 64, 96, 128, 224, 256, 512 at the J of csrc/wst_configs.inc, L <= 8), otherwise
+ *                            WST2D_ENGINE_GEMM_SIMT
  *   WST2D_ENGINE_FFT         the fused cascade or WST2D_ERR_UNSUPPORTED
  *   WST2D_ENGINE_GEMM_SIMT   every DFT of the cascade as a dense DFT-matrix product on the fp32 pipe (any size)
  *   WST2D_ENGINE_GEMM_TF32X3 the same products on the tensor cores as 3xTF32 (fp32-level accuracy)

@@ -21,7 +21,7 @@ TOL = 1e-4
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 CONFIGS = [(32, 2, 8), (64, 3, 8), (128, 4, 8), (128, 2, 8), (32, 3, 6),
            (32, 1, 8), (64, 2, 8), (128, 3, 8), (32, 4, 8), (64, 4, 8),
-           (48, 3, 8), (96, 2, 8), (96, 4, 8)]
+           (48, 3, 8), (96, 2, 8), (96, 4, 8), (48, 2, 8), (96, 3, 8)]
 
 
 def floored_rel(a, b):
@@ -167,6 +167,19 @@ def test_256x256_patches(wst, J, N, h):
     f = feats[:2, 0].cpu().numpy()
     assert floored_rel(f[:, 0], ref.mean(axis=(-2, -1))) <= TOL
     assert floored_rel(f[:, 1], ref.std(axis=(-2, -1))) <= TOL
+
+
+def test_224x224_J3(wst):
+    """224x224 J=3 (padded side 240 = 16*15, 28 x 28 output maps): hybrid global-workspace cascade."""
+    rng = np.random.default_rng(224)
+    x = (rng.integers(0, 256, (2, 1, 224, 224)) / 255.0).astype(np.float32)
+    plan = wst.get_plan(224, 224, 3, 8)
+    assert (plan.h, plan.Hp, plan.engine) == (28, 240, "fft")
+    feats, maps = plan.forward(torch.from_numpy(x).cuda(), True, True)
+    ref = oracle64(224, 3, 8)(x[:, 0])
+    K = ref.shape[1]
+    assert_parity(maps[:, 0].cpu().numpy().reshape(2, K, -1), ref.reshape(2, K, -1), 3, 8, what="224x224 J=3 maps")
+    assert_parity(feats[:, 0, 0].cpu().numpy(), ref.mean(axis=(-2, -1)), 3, 8, what="224x224 J=3 mean")
 
 
 def test_max_order_1(wst):

@@ -11,7 +11,7 @@ from tests.parity import parity_report
 
 rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 ncases = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-fused = [(32, 1), (32, 2), (32, 3), (32, 4), (64, 2), (64, 3), (64, 4), (128, 2), (128, 3), (128, 4), (48, 3), (96, 2), (96, 4)]
+fused = [(32, 1), (32, 2), (32, 3), (32, 4), (64, 2), (64, 3), (64, 4), (128, 2), (128, 3), (128, 4), (48, 3), (96, 2), (96, 4), (48, 2), (96, 3)]
 worst, fails = 0.0, 0
 for case in range(ncases):
     if case % 2 == 0:                                   # a compiled cascade, random batch geometry

@@ -45,7 +45,7 @@ GLOBAL_OVERRIDES = {
     # 256 x 256: one 768-thread CTA per SM, levels <= 144^2 in a 216 KB shared-memory region, and a 1 MB workspace per CTA
     # (one level-0 array at a time: the 148 workspaces stay in L2).  5.0 / 5.1 / 5.8 k -> 6.5 / 7.8 / 8.6 k patches/s at J=2/3/4.
     (264, 2): (768, 27000, 1 << 17), (272, 3): (768, 27000, 1 << 17), (288, 4): (768, 27000, 1 << 17),
-    (320, 5): (640, 27000, 1 << 17),
+    (320, 5): (640, 27000, 1 << 17), (240, 3): (768, 27000, 1 << 17),
     # 512 x 512 J=5: two 256-thread CTAs per SM, levels <= 72^2 in a 100 KB region each (+5 %; one wide CTA loses 10-16 %
     # on the 576^2 and 288^2 levels, which stay in the workspace and do not fit L2 at any budget)
     (576, 5): (256, 12500, 1 << 20),

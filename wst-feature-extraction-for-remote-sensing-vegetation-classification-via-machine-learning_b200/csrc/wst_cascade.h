@@ -201,7 +201,9 @@ struct Cfg {
     static constexpr int BUDGET = WS_GLOBAL_ ? kGlobalCfloats : kSmemCfloats;
     static constexpr int NS = N >> J;           // side of the subsampled (still padded) output grid
     static constexpr int HOUT = NS - 2;         // kept outputs per side after unpad [1:-1]
-    static constexpr int HP = (HOUT + 3) & ~3;  // padded to float4
+    // row length of the low-pass operator tables: padded to float4, and to two float4s from 8 outputs on (the dense
+    // low-pass takes its outputs eight at a time)
+    static constexpr int HP = HOUT >= 8 ? (HOUT + 7) & ~7 : (HOUT + 3) & ~3;
     static_assert((N >> J) << J == N, "padded size must be a multiple of 2^J");
     static_assert(HOUT >= 1, "empty output");
 
@@ -1160,7 +1162,7 @@ WST_D void lowpass_maps_dense(Exec& ex, cfloat* z, int ZS, int narr, const float
     constexpr int GO1 = HOUT >= 8 ? 8 : HP, NG1 = (HOUT + GO1 - 1) / GO1;      // phase 1: outputs per thread (float4s of G)
     constexpr int NG2 = HP / 4;                                                // phase 2: one float4 of outputs per thread
     static_assert(PT * M <= 2 * HALF * P && GO1 % 4 == 0, "low-pass scratch must fit in the dead half of the array");
-    static_assert(HOUT < 8 || HOUT % 8 == 0, "output side must be below 8 or a multiple of 8");
+    static_assert(HOUT < 8 || HP % 8 == 0, "operator rows must hold whole groups of eight outputs");
     // phase LP1: T[y][i] = sum_x Gr[x][i] * U[x][y]; thread = (array, group of GO1 outputs i, column slot y), the
     // G rows are warp-uniform (broadcast) vector loads, the U column is read as (row x, row x + M/2) pairs.
     ex.template phase<PK_LP1 * 8 + LV>([&](int tid) {
