@@ -34,6 +34,9 @@ GLOBAL_VARIANT_HYBRID = int(os.environ.get("WST_BUILD_HYBRID", 0))
 # {(N, J): (threads per CTA, data-region budget in cfloats)}; small sides leave room for several CTAs per SM, whose
 # barrier waits then overlap.  WST_BUILD_SHARED="N:J:threads:budget,..." overrides for tuning runs.
 SHARED_OVERRIDES = {(40, 2): (160, 6000), (80, 3): (320, 12000)}     # four / two narrower CTAs per SM (measured best)
+# Per-configuration tuning knobs of csrc/wst_cascade.h that measured better for that configuration only
+# (the sparse / dense-many products with hoisted spectrum rows: +2.4 % at 64x64 J=3, -1.2 % at 128x128 J=4)
+CONFIG_DEFS = {(80, 3): ["-DWST_OPT_SPARSEROW=1"]}
 for _item in filter(None, os.environ.get("WST_BUILD_SHARED", "").split(",")):
     _n, _j, _t, _b = (int(v) for v in _item.split(":"))
     SHARED_OVERRIDES[(_n, _j)] = (_t, _b)
@@ -122,6 +125,8 @@ def build_library(force=False, verbose=False):
             nt, budget = SHARED_OVERRIDES[(n, j)]
             o = os.path.join(OBJ, "wst_cfg_%d_%d_t%d_b%d.o" % (n, j, nt, budget))
             defs += ["-DWST_CFG_NT=%d" % nt, "-DWST_SMEM_BUDGET=%d" % budget]
+        if (n, j) in CONFIG_DEFS and not _DEFS:
+            defs += CONFIG_DEFS[(n, j)]
         objs.append(o)
         jobs.append(([nvcc] + NVCC_FLAGS + extra + defs + ["-c", os.path.join(CSRC, "wst_cfg_inst.cu"), "-o", o], verbose))
     if not force:                       # objects carry their variant in the name: recompile only what is out of date

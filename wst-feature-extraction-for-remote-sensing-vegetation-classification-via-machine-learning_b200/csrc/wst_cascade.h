@@ -178,6 +178,23 @@ WST_CX bool lp_banded(int m, int hout, int level) {
 #ifndef WST_OPT_ROWSEQ
 #define WST_OPT_ROWSEQ 0
 #endif
+//   WST_OPT_PAIRHALF  dense few-orientation products pair the outputs (l, l + MC/2) instead of (l, l + 1): consecutive
+//                     lanes then read consecutive spectrum samples (no two-way bank conflicts: these loads and stores
+//                     were 35 % of the kernel's conflict replays) and whether an alias comes from the stored half
+//                     spectrum or from its Hermitian mirror is known at compile time (no branches)
+#ifndef WST_OPT_PAIRHALF
+#define WST_OPT_PAIRHALF 1
+#endif
+//   WST_OPT_HERMSEL   Hermitian lookups select row, column and sign arithmetically instead of branching
+#ifndef WST_OPT_HERMSEL
+#define WST_OPT_HERMSEL 0
+#endif
+//   WST_OPT_SPARSEROW the sparse products compute the two spectrum row pointers (row k and its mirror -k) once per alias
+//                     row; with all F column aliases visited (F = 4) the side of the half spectrum is a compile-time
+//                     property of the alias, otherwise row, column and sign are selected without a branch
+#ifndef WST_OPT_SPARSEROW
+#define WST_OPT_SPARSEROW 0
+#endif
 #ifndef WST_STAGE_TC_MAX
 #define WST_STAGE_TC_MAX 16
 #endif
@@ -925,6 +942,13 @@ WST_D void rfft2_from_pairs(Exec& ex, cfloat* z, int ZS, cfloat* uh, int narr, c
 template <int M>
 WST_D cfloat herm_get(const cfloat* uh, int k, int l) {
     constexpr int PH = M / 2 + 1;
+    if constexpr (WST_OPT_HERMSEL) {
+        const bool dir = l <= M / 2;
+        const int kk = dir ? k : (k == 0 ? 0 : M - k), ll = dir ? l : M - l;
+        cfloat v = uh[Fft1<M>::pi(kk) * PH + ll];
+        v.y = dir ? v.y : -v.y;
+        return v;
+    }
     if (l <= M / 2) return uh[Fft1<M>::pi(k) * PH + l];
     int kk = (k == 0) ? 0 : M - k;
     cfloat v = uh[Fft1<M>::pi(kk) * PH + (M - l)];
@@ -981,7 +1005,46 @@ WST_D void product_fold(int tid, const cfloat* uh, const float* filt, int rows, 
     constexpr int F = MP / MC, PC = MC + 1, AS = MC * (MC + 1);
     constexpr bool SPARSE = F >= 4;
     constexpr float scale = 1.0f / ((float)F * (float)F * (float)MC * (float)MC);
-    if constexpr (!SPARSE && GS <= 2 && MC % 2 == 0 && MP % 4 == 0) {
+    if constexpr (WST_OPT_PAIRHALF && !SPARSE && GS <= 2 && MC % 2 == 0 && MP % 4 == 0) {
+        constexpr int HM = MP / 2, PH = MP / 2 + 1, HC = MC / 2;
+        static_assert(HM % HC == 0, "alias columns must fall wholly on one side of the half spectrum");
+        for (int o = tid; o < MC * HC; o += NT) {
+            const int lc = o % HC, kc = o / HC;
+            float ar[2][GS], ai[2][GS];
+            static_for<0, 2 * GS>([&](auto E) { ar[decltype(E)::value / GS][decltype(E)::value % GS] = 0.f;
+                                                ai[decltype(E)::value / GS][decltype(E)::value % GS] = 0.f; });
+            static_for<0, F>([&](auto A) {
+                constexpr int a = decltype(A)::value;
+                const int k = kc + a * MC;
+                const cfloat* rd = uh + Fft1<MP>::pi(k) * PH;                       // row k, columns 0..MP/2
+                const cfloat* rm = uh + Fft1<MP>::pi(k == 0 ? 0 : MP - k) * PH;       // row -k for the mirrored half
+                const float* frow = filt + (size_t)k * MP * GS;
+                static_for<0, 2 * F>([&](auto Q) {
+                    constexpr int q = decltype(Q)::value, p = q % 2, off = (q / 2) * MC + p * HC;   // column l = lc + off
+                    constexpr bool MIR = off >= HM;            // every lc < HC lands on the same side of column MP/2
+                    const int l = lc + off;
+                    const cfloat u = MIR ? rm[MP - l] : rd[l];                  // U(k, l) = conj(U(-k, -l))
+                    float w[GS];
+                    if constexpr (GS == 2) { const float2 t = *reinterpret_cast<const float2*>(frow + (size_t)l * 2); w[0] = t.x; w[1] = t.y; }
+                    else w[0] = frow[l];
+                    static_for<0, GS>([&](auto G) {
+                        constexpr int g = decltype(G)::value;
+                        ar[p][g] += u.x * w[g];
+                        if constexpr (MIR) ai[p][g] -= u.y * w[g]; else ai[p][g] += u.y * w[g];
+                    });
+                });
+            });
+            cfloat* orow = out + Fft1<MC>::pi(kc) * PC;
+            static_for<0, 2>([&](auto Pp) {
+                constexpr int p = decltype(Pp)::value;
+                cfloat* op = orow + Fft1<MC>::pi(lc + p * HC);
+                static_for<0, GS>([&](auto G) {
+                    constexpr int g = decltype(G)::value;
+                    op[g * AS] = cmake(ar[p][g] * scale, ai[p][g] * scale);
+                });
+            });
+        }
+    } else if constexpr (!SPARSE && GS <= 2 && MC % 2 == 0 && MP % 4 == 0) {
         // dense, few orientations per pass (the 80 x 80 children and the full-resolution parents, where only
         // one or two arrays fit): these phases are issue-bound and the index arithmetic is shared by only GS
         // accumulators, so each thread takes two adjacent outputs (l even, l+1): one 8/16-byte filter load and
@@ -1086,7 +1149,13 @@ WST_D void product_fold(int tid, const cfloat* uh, const float* filt, int rows, 
                     constexpr int sl = decltype(S)::value;
                     const int k = kc[ui] + (sl / F) * MC, l = lc[ui] + (sl % F) * MC;
                     load_filter_vec<MP, GS>(filt + ((size_t)k * MP + l) * GS, w[ui][sl]);
-                    u[ui][sl] = herm_get<MP>(uh, k, l);
+                    if constexpr (WST_OPT_SPARSEROW && F == 2) {
+                        // fold by two: alias column b = 0 lies in the stored half, b = 1 in the mirrored half, for every output
+                        if constexpr (sl % F == 0) u[ui][sl] = uh[Fft1<MP>::pi(k) * (MP / 2 + 1) + l];
+                        else { const cfloat v = uh[Fft1<MP>::pi(k == 0 ? 0 : MP - k) * (MP / 2 + 1) + (MP - l)]; u[ui][sl] = cmake(v.x, -v.y); }
+                    } else {
+                        u[ui][sl] = herm_get<MP>(uh, k, l);
+                    }
                 });
             });
             static_for<0, U>([&](auto Uc) {
@@ -1122,15 +1191,32 @@ WST_D void product_fold(int tid, const cfloat* uh, const float* filt, int rows, 
             for (int ia = 0; ia < ra.count; ++ia) {
                 int a = ra.first + ia; a -= a >= F ? F : 0;
                 const int k = kc + a * MC;
+                [[maybe_unused]] const cfloat* rd = uh + Fft1<MP>::pi(k) * (MP / 2 + 1);
+                [[maybe_unused]] const cfloat* rm = uh + Fft1<MP>::pi(k == 0 ? 0 : MP - k) * (MP / 2 + 1);
                 for (int ib0 = 0; ib0 < rb.count; ib0 += NB) {
                     float w[NB][GS];
                     cfloat u[NB];
                     static_for<0, NB>([&](auto B) {
                         constexpr int bi = decltype(B)::value;
-                        int b = rb.first + ib0 + bi; b -= b >= F ? F : 0;
-                        const int l = lc + b * MC;
-                        load_filter_vec<MP, GS>(filt + ((size_t)k * MP + l) * GS, w[bi]);
-                        u[bi] = herm_get<MP>(uh, k, l);
+                        if constexpr (WST_OPT_SPARSEROW && NB == F) {
+                            // every alias is visited, in order: the side of column MP/2 is known at compile time
+                            constexpr bool MIR = bi * MC >= MP / 2;
+                            const int l = lc + bi * MC;
+                            load_filter_vec<MP, GS>(filt + ((size_t)k * MP + l) * GS, w[bi]);
+                            if constexpr (MIR) { const cfloat v = rm[MP - l]; u[bi] = cmake(v.x, -v.y); }
+                            else u[bi] = rd[l];
+                        } else {
+                            int b = rb.first + ib0 + bi; b -= b >= F ? F : 0;
+                            const int l = lc + b * MC;
+                            load_filter_vec<MP, GS>(filt + ((size_t)k * MP + l) * GS, w[bi]);
+                            if constexpr (WST_OPT_SPARSEROW) {
+                                const bool dir = l <= MP / 2;
+                                const cfloat v = dir ? rd[l] : rm[MP - l];
+                                u[bi] = cmake(v.x, dir ? v.y : -v.y);
+                            } else {
+                                u[bi] = herm_get<MP>(uh, k, l);
+                            }
+                        }
                     });
                     static_for<0, NB>([&](auto B) {
                         constexpr int bi = decltype(B)::value;
