@@ -189,9 +189,10 @@ WST_CX bool lp_banded(int m, int hout, int level) {
 #ifndef WST_OPT_HERMSEL
 #define WST_OPT_HERMSEL 0
 #endif
-//   WST_OPT_SPARSEROW the sparse products compute the two spectrum row pointers (row k and its mirror -k) once per alias
-//                     row; with all F column aliases visited (F = 4) the side of the half spectrum is a compile-time
-//                     property of the alias, otherwise row, column and sign are selected without a branch
+//   WST_OPT_SPARSEROW bit mask.  1: sparse products that visit all F column aliases (F = 4) compute the two spectrum row
+//                     pointers (row k and its mirror -k) once per alias row and know the side of the half spectrum of
+//                     each alias at compile time; 2: the other sparse products (F = 8) select row, column and sign
+//                     without a branch; 4: dense many-orientation products at fold 2 know the side at compile time
 #ifndef WST_OPT_SPARSEROW
 #define WST_OPT_SPARSEROW 0
 #endif
@@ -1149,7 +1150,7 @@ WST_D void product_fold(int tid, const cfloat* uh, const float* filt, int rows, 
                     constexpr int sl = decltype(S)::value;
                     const int k = kc[ui] + (sl / F) * MC, l = lc[ui] + (sl % F) * MC;
                     load_filter_vec<MP, GS>(filt + ((size_t)k * MP + l) * GS, w[ui][sl]);
-                    if constexpr (WST_OPT_SPARSEROW && F == 2) {
+                    if constexpr ((WST_OPT_SPARSEROW & 4) && F == 2) {
                         // fold by two: alias column b = 0 lies in the stored half, b = 1 in the mirrored half, for every output
                         if constexpr (sl % F == 0) u[ui][sl] = uh[Fft1<MP>::pi(k) * (MP / 2 + 1) + l];
                         else { const cfloat v = uh[Fft1<MP>::pi(k == 0 ? 0 : MP - k) * (MP / 2 + 1) + (MP - l)]; u[ui][sl] = cmake(v.x, -v.y); }
@@ -1198,7 +1199,7 @@ WST_D void product_fold(int tid, const cfloat* uh, const float* filt, int rows, 
                     cfloat u[NB];
                     static_for<0, NB>([&](auto B) {
                         constexpr int bi = decltype(B)::value;
-                        if constexpr (WST_OPT_SPARSEROW && NB == F) {
+                        if constexpr ((WST_OPT_SPARSEROW & 1) && NB == F) {
                             // every alias is visited, in order: the side of column MP/2 is known at compile time
                             constexpr bool MIR = bi * MC >= MP / 2;
                             const int l = lc + bi * MC;
@@ -1209,7 +1210,7 @@ WST_D void product_fold(int tid, const cfloat* uh, const float* filt, int rows, 
                             int b = rb.first + ib0 + bi; b -= b >= F ? F : 0;
                             const int l = lc + b * MC;
                             load_filter_vec<MP, GS>(filt + ((size_t)k * MP + l) * GS, w[bi]);
-                            if constexpr (WST_OPT_SPARSEROW) {
+                            if constexpr ((WST_OPT_SPARSEROW & 2) != 0) {
                                 const bool dir = l <= MP / 2;
                                 const cfloat v = dir ? rd[l] : rm[MP - l];
                                 u[bi] = cmake(v.x, dir ? v.y : -v.y);
