@@ -196,6 +196,12 @@ WST_CX bool lp_banded(int m, int hout, int level) {
 #ifndef WST_OPT_SPARSEROW
 #define WST_OPT_SPARSEROW 0
 #endif
+//   WST_OPT_LPPAIR    the first contraction of the dense low-pass takes two columns (y, y + M/2) per thread: every
+//                     (warp-uniform) vector load of the operator feeds twice the FMAs; the phase is bound by
+//                     shared-memory wavefronts, not by arithmetic
+#ifndef WST_OPT_LPPAIR
+#define WST_OPT_LPPAIR 1
+#endif
 #ifndef WST_STAGE_TC_MAX
 #define WST_STAGE_TC_MAX 16
 #endif
@@ -1252,6 +1258,42 @@ WST_D void lowpass_maps_dense(Exec& ex, cfloat* z, int ZS, int narr, const float
     static_assert(HOUT < 8 || HP % 8 == 0, "operator rows must hold whole groups of eight outputs");
     // phase LP1: T[y][i] = sum_x Gr[x][i] * U[x][y]; thread = (array, group of GO1 outputs i, column slot y), the
     // G rows are warp-uniform (broadcast) vector loads, the U column is read as (row x, row x + M/2) pairs.
+    if constexpr (WST_OPT_LPPAIR && M % 2 == 0) {
+        ex.template phase<PK_LP1 * 8 + LV>([&](int tid) {
+            constexpr int HM2 = M / 2;
+            const int total = narr * NG1 * HM2;
+            for (int b = tid; b < total; b += NT) {
+                const int y = b % HM2, r = b / HM2;
+                const int q = r % NG1, g = r / NG1;
+                const cfloat* zp = z + g * ZS + y;
+                const float* g0 = gr + q * GO1;
+                float acc[2][GO1];
+                static_for<0, 2 * GO1>([&](auto I) { acc[decltype(I)::value / GO1][decltype(I)::value % GO1] = 0.f; });
+#pragma unroll 2
+                for (int x = 0; x < HALF; ++x) {
+                    const cfloat v0 = zp[x * P], v1 = zp[x * P + HM2];
+                    static_for<0, GO1 / 4>([&](auto Q) {
+                        constexpr int k = decltype(Q)::value;
+                        const float4 a = *reinterpret_cast<const float4*>(g0 + x * HP + 4 * k);
+                        const float4 d = *reinterpret_cast<const float4*>(g0 + (x + HALF) * HP + 4 * k);
+                        acc[0][4 * k + 0] += a.x * v0.x; acc[0][4 * k + 0] += d.x * v0.y;
+                        acc[0][4 * k + 1] += a.y * v0.x; acc[0][4 * k + 1] += d.y * v0.y;
+                        acc[0][4 * k + 2] += a.z * v0.x; acc[0][4 * k + 2] += d.z * v0.y;
+                        acc[0][4 * k + 3] += a.w * v0.x; acc[0][4 * k + 3] += d.w * v0.y;
+                        acc[1][4 * k + 0] += a.x * v1.x; acc[1][4 * k + 0] += d.x * v1.y;
+                        acc[1][4 * k + 1] += a.y * v1.x; acc[1][4 * k + 1] += d.y * v1.y;
+                        acc[1][4 * k + 2] += a.z * v1.x; acc[1][4 * k + 2] += d.z * v1.y;
+                        acc[1][4 * k + 3] += a.w * v1.x; acc[1][4 * k + 3] += d.w * v1.y;
+                    });
+                }
+                float* tp = reinterpret_cast<float*>(z + g * ZS + HALF * P) + y * PT + q * GO1;
+                static_for<0, GO1>([&](auto I) {
+                    constexpr int i = decltype(I)::value;
+                    if (q * GO1 + i < HOUT) { tp[i] = acc[0][i]; tp[HM2 * PT + i] = acc[1][i]; }
+                });
+            }
+        });
+    } else
     ex.template phase<PK_LP1 * 8 + LV>([&](int tid) {
         const int total = narr * NG1 * M;
         for (int b = tid; b < total; b += NT) {
