@@ -119,6 +119,64 @@ def test_torch_library_op(wst):
     assert torch.allclose(compiled(x), a * 2.0)
 
 
+@pytest.mark.parametrize("M,J", [(32, 2), (64, 3), (128, 2)])
+def test_ticket_scheduler_equals_fixed_stride(wst, M, J):
+    """Many waves: the signals after each CTA's first one come from a device-wide ticket counter.  Every signal is
+    processed exactly once and its numbers do not depend on which CTA ran it: bit-equal to the fixed-stride assignment
+    (WST_STATIC_SCHED=1), call after call (the counter is re-zeroed per launch)."""
+    import os
+    plan = wst.get_plan(M, M, J)
+    nsig = 20 * plan.grid + 3 if M <= 64 else 17 * plan.grid + 100
+    g = torch.Generator(device="cuda").manual_seed(M + J)
+    x = torch.randint(0, 256, (nsig, 1, M, M), device="cuda", generator=g, dtype=torch.int32).float().div_(255.0)
+    f1 = plan.forward(x)[0].clone()
+    f2 = plan.forward(x)[0].clone()
+    os.environ["WST_STATIC_SCHED"] = "1"
+    try:
+        f_ref = plan.forward(x)[0].clone()
+    finally:
+        del os.environ["WST_STATIC_SCHED"]
+    torch.cuda.synchronize()
+    assert torch.equal(f1, f_ref) and torch.equal(f2, f_ref)
+
+
+@pytest.mark.parametrize("M,J,tail", [(32, 2, 1), (64, 3, 7), (128, 4, 4), (128, 2, 70)])
+def test_ragged_last_wave_runs_split(wst, M, J, tail):
+    """nsig = 2 * grid + tail: the tail signals run as a second, split launch instead of leaving grid - tail CTAs idle
+    for a whole signal time.  Same features and maps as one launch over everything, bit for bit — float32 planes, uint8
+    HWC pixels (signal offset inside a patch) and the host-buffer path."""
+    import os
+    plan = wst.get_plan(M, M, J)
+    nsig = 2 * plan.grid + tail            # (the split tail is kept for batches of up to 16 waves)
+    rng = np.random.default_rng(M + J + tail)
+    x = torch.from_numpy((rng.integers(0, 256, (nsig, 1, M, M)) / 255.0).astype(np.float32)).cuda()
+    two = tail * 2 <= plan.grid
+    assert plan.launch_count(nsig, 1) == (2 if two else 1)
+    f_tail, m_tail = plan.forward(x, True, True)
+    f_only = plan.forward(x)[0]
+    f_host = plan.forward_host(x.cpu())
+    os.environ["WST_NO_TAIL_SPLIT"] = "1"
+    try:
+        assert plan.launch_count(nsig, 1) == 1
+        f_ref, m_ref = plan.forward(x, True, True)
+    finally:
+        del os.environ["WST_NO_TAIL_SPLIT"]
+    torch.cuda.synchronize()
+    assert torch.equal(m_tail, m_ref)
+    assert torch.equal(f_tail, f_ref) and torch.equal(f_only, f_ref)
+    assert np.array_equal(np.asarray(f_host).reshape(nsig, -1), f_ref.reshape(nsig, -1).cpu().numpy())
+    if M <= 64:                                     # uint8 HWC: 3 signals per patch, the tail starts inside the batch
+        B = (nsig + 2) // 3
+        u8 = torch.from_numpy(rng.integers(0, 256, (B, M, M, 3), dtype=np.uint8)).cuda()
+        f_u8 = plan.forward(u8)[0]
+        os.environ["WST_NO_TAIL_SPLIT"] = "1"
+        try:
+            f_u8_ref = plan.forward(u8)[0]
+        finally:
+            del os.environ["WST_NO_TAIL_SPLIT"]
+        assert torch.equal(f_u8, f_u8_ref)
+
+
 @pytest.mark.parametrize("M,J,B", [(128, 2, 1), (128, 4, 2), (64, 3, 5), (32, 2, 1)])
 def test_small_batches_split_signals_across_ctas(wst, M, J, B):
     """The reference calls the extractor one image at a time (train_and_save_model.py:486-488): with fewer signals than

@@ -202,6 +202,18 @@ WST_CX bool lp_banded(int m, int hout, int level) {
 #ifndef WST_OPT_LPPAIR
 #define WST_OPT_LPPAIR 1
 #endif
+//   WST_OPT_L2HINT   bit mask, global-workspace variant only.  1: filter loads of the product phases carry an L2
+//                     evict_last policy (the bank is re-read by every CTA for every signal; without it the workspaces
+//                     streaming through L2 push it out to HBM).  2: tile loads of the staged passes carry evict_first.
+//                     4: tile stores carry evict_first.  8: product outputs written to the workspace carry evict_first.
+#ifndef WST_OPT_L2HINT
+#define WST_OPT_L2HINT 9
+#endif
+//   WST_OPT_DYNSCHED  signals after a CTA's first one come from a device-wide ticket counter instead of a fixed stride
+//                     (run_cascade in wst_cfg_inst.cu)
+#ifndef WST_OPT_DYNSCHED
+#define WST_OPT_DYNSCHED 1
+#endif
 #ifndef WST_STAGE_TC_MAX
 #define WST_STAGE_TC_MAX 16
 #endif
@@ -406,10 +418,12 @@ struct InputDesc {
     int mode, C;
     int Himg, Wimg, nx, sy, sx;
     long long tile0;
+    long long sig0;    // signal 0 of the launch is signal sig0 of the described input (a launch over the tail of a batch)
 };
 
 WST_D SignalSrc signal_source(const InputDesc& in, long long s, int H, int W) {
     SignalSrc src;
+    s += in.sig0;
     src.f32 = nullptr; src.u8 = nullptr; src.stride = 1; src.pitch = W;
     if (in.mode == 1) {
         const long long b = s / in.C;
@@ -780,13 +794,68 @@ WST_D void lowpass_reduce(Exec& ex, cfloat* base, int narr, int AS, const float*
     });
 }
 
+// L2 eviction-priority hints (createpolicy + .L2::cache_hint); host emulation: plain accesses.
+template <bool LAST> WST_D unsigned long long l2_policy() {
+#ifdef __CUDA_ARCH__
+    unsigned long long pol;
+    if constexpr (LAST) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+#else
+    return 0;
+#endif
+}
+// Filter-bank loads (read-only for the kernel's lifetime).  FH: keep the line in L2 (evict_last).
+template <bool FH> WST_D float ldf1(const float* p) {
+#ifdef __CUDA_ARCH__
+    if constexpr (FH) { float v; asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(l2_policy<true>())); return v; }
+#endif
+    return *p;
+}
+template <bool FH> WST_D float2 ldf2(const float* p) {
+#ifdef __CUDA_ARCH__
+    if constexpr (FH) { float2 v; asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(l2_policy<true>())); return v; }
+#endif
+    return *reinterpret_cast<const float2*>(p);
+}
+template <bool FH> WST_D float4 ldf4(const float* p) {
+#ifdef __CUDA_ARCH__
+    if constexpr (FH) { float4 v; asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(l2_policy<true>())); return v; }
+#endif
+    return *reinterpret_cast<const float4*>(p);
+}
+// Product outputs written to the workspace (OH: evict_first — a group of arrays is written in full before its first tile
+// is read back).
+template <bool OH> WST_D void prod_store(cfloat* dst, cfloat v) {
+#ifdef __CUDA_ARCH__
+    if constexpr (OH) {
+        asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(dst), "f"(v.x), "f"(v.y), "l"(l2_policy<false>()) : "memory");
+        return;
+    }
+#endif
+    *dst = v;
+}
+// Workspace tile stores of the staged passes (the tile is not read again before the rest of the array has streamed by).
+WST_D void stage_store(cfloat* dst_global, cfloat v) {
+#ifdef __CUDA_ARCH__
+    if constexpr ((WST_OPT_L2HINT & 4) != 0) {
+        asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(dst_global), "f"(v.x), "f"(v.y), "l"(l2_policy<false>()) : "memory");
+        return;
+    }
+#endif
+    *dst_global = v;
+}
+
 // Tile loads of the staged passes: asynchronous 8-byte global -> shared copies (LDGSTS), so that a thread's whole
 // share of the tile is in flight at once instead of one register round trip after another; stage_copy_wait() closes the
 // phase that issued them.  (Host emulation: plain copies.)
 WST_D void stage_copy(cfloat* dst_shared, const cfloat* src_global) {
 #ifdef __CUDA_ARCH__
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst_shared);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src_global) : "memory");
+    if constexpr ((WST_OPT_L2HINT & 2) != 0)
+        asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;" ::"r"(d), "l"(src_global), "l"(l2_policy<false>()) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src_global) : "memory");
 #else
     *dst_shared = *src_global;
 #endif
@@ -991,23 +1060,23 @@ WST_D AliasRun alias_run(int base, int packed) {
 //          starting at the first alias inside (extra ones only add exact zeros' worth of tail), so the loads
 //          of a row are independent and in flight together — these phases are L2-latency bound.
 //   out  : GS arrays of MC x MC (pitch MC+1, stride MC*(MC+1))
-template <int MP, int GS>
+template <int MP, int GS, bool FH = false>
 WST_D void load_filter_vec(const float* fp, float (&w)[GS]) {
     if constexpr (GS % 4 == 0) {
         static_for<0, GS / 4>([&](auto Q) {
             constexpr int q = decltype(Q)::value;
-            float4 t = *reinterpret_cast<const float4*>(fp + 4 * q);
+            float4 t = ldf4<FH>(fp + 4 * q);
             w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
         });
     } else if constexpr (GS == 2) {
-        float2 t = *reinterpret_cast<const float2*>(fp);
+        float2 t = ldf2<FH>(fp);
         w[0] = t.x; w[1] = t.y;
     } else {
-        static_for<0, GS>([&](auto G) { w[decltype(G)::value] = fp[decltype(G)::value]; });
+        static_for<0, GS>([&](auto G) { w[decltype(G)::value] = ldf1<FH>(fp + decltype(G)::value); });
     }
 }
 
-template <int MP, int MC, int GS, int NT>
+template <int MP, int MC, int GS, int NT, bool FH = false, bool OH = false>
 WST_D void product_fold(int tid, const cfloat* uh, const float* filt, int rows, int cols, cfloat* out) {
     constexpr int F = MP / MC, PC = MC + 1, AS = MC * (MC + 1);
     constexpr bool SPARSE = F >= 4;
@@ -1032,8 +1101,8 @@ WST_D void product_fold(int tid, const cfloat* uh, const float* filt, int rows, 
                     const int l = lc + off;
                     const cfloat u = MIR ? rm[MP - l] : rd[l];                  // U(k, l) = conj(U(-k, -l))
                     float w[GS];
-                    if constexpr (GS == 2) { const float2 t = *reinterpret_cast<const float2*>(frow + (size_t)l * 2); w[0] = t.x; w[1] = t.y; }
-                    else w[0] = frow[l];
+                    if constexpr (GS == 2) { const float2 t = ldf2<FH>(frow + (size_t)l * 2); w[0] = t.x; w[1] = t.y; }
+                    else w[0] = ldf1<FH>(frow + l);
                     static_for<0, GS>([&](auto G) {
                         constexpr int g = decltype(G)::value;
                         ar[p][g] += u.x * w[g];
@@ -1047,7 +1116,7 @@ WST_D void product_fold(int tid, const cfloat* uh, const float* filt, int rows, 
                 cfloat* op = orow + Fft1<MC>::pi(lc + p * HC);
                 static_for<0, GS>([&](auto G) {
                     constexpr int g = decltype(G)::value;
-                    op[g * AS] = cmake(ar[p][g] * scale, ai[p][g] * scale);
+                    prod_store<OH>(op + g * AS, cmake(ar[p][g] * scale, ai[p][g] * scale));
                 });
             });
         }
@@ -1067,10 +1136,10 @@ WST_D void product_fold(int tid, const cfloat* uh, const float* filt, int rows, 
                 constexpr int sl = decltype(S)::value, a = sl / F, b = sl % F;
                 const float* fp = fb + ((size_t)a * MC * MP + b * MC) * GS;
                 if constexpr (GS == 2) {
-                    float4 t = *reinterpret_cast<const float4*>(fp);
+                    float4 t = ldf4<FH>(fp);
                     w[sl][0][0] = t.x; w[sl][0][1] = t.y; w[sl][1][0] = t.z; w[sl][1][1] = t.w;
                 } else {
-                    float2 t = *reinterpret_cast<const float2*>(fp);
+                    float2 t = ldf2<FH>(fp);
                     w[sl][0][0] = t.x; w[sl][1][0] = t.y;
                 }
             });
@@ -1129,7 +1198,7 @@ WST_D void product_fold(int tid, const cfloat* uh, const float* filt, int rows, 
                 cfloat* op = orow + Fft1<MC>::pi(lc + p);
                 static_for<0, GS>([&](auto G) {
                     constexpr int g = decltype(G)::value;
-                    op[g * AS] = cmake(ar[p][g] * scale, ai[p][g] * scale);
+                    prod_store<OH>(op + g * AS, cmake(ar[p][g] * scale, ai[p][g] * scale));
                 });
             });
         }
@@ -1155,7 +1224,7 @@ WST_D void product_fold(int tid, const cfloat* uh, const float* filt, int rows, 
                 static_for<0, F * F>([&](auto S) {
                     constexpr int sl = decltype(S)::value;
                     const int k = kc[ui] + (sl / F) * MC, l = lc[ui] + (sl % F) * MC;
-                    load_filter_vec<MP, GS>(filt + ((size_t)k * MP + l) * GS, w[ui][sl]);
+                    load_filter_vec<MP, GS, FH>(filt + ((size_t)k * MP + l) * GS, w[ui][sl]);
                     if constexpr ((WST_OPT_SPARSEROW & 4) && F == 2) {
                         // fold by two: alias column b = 0 lies in the stored half, b = 1 in the mirrored half, for every output
                         if constexpr (sl % F == 0) u[ui][sl] = uh[Fft1<MP>::pi(k) * (MP / 2 + 1) + l];
@@ -1181,7 +1250,7 @@ WST_D void product_fold(int tid, const cfloat* uh, const float* filt, int rows, 
                     cfloat* op = out + Fft1<MC>::pi(kc[ui]) * PC + Fft1<MC>::pi(lc[ui]);
                     static_for<0, GS>([&](auto G) {
                         constexpr int g = decltype(G)::value;
-                        op[g * AS] = cmake(ar[g] * scale, ai[g] * scale);
+                        prod_store<OH>(op + g * AS, cmake(ar[g] * scale, ai[g] * scale));
                     });
                 }
             });
@@ -1209,13 +1278,13 @@ WST_D void product_fold(int tid, const cfloat* uh, const float* filt, int rows, 
                             // every alias is visited, in order: the side of column MP/2 is known at compile time
                             constexpr bool MIR = bi * MC >= MP / 2;
                             const int l = lc + bi * MC;
-                            load_filter_vec<MP, GS>(filt + ((size_t)k * MP + l) * GS, w[bi]);
+                            load_filter_vec<MP, GS, FH>(filt + ((size_t)k * MP + l) * GS, w[bi]);
                             if constexpr (MIR) { const cfloat v = rm[MP - l]; u[bi] = cmake(v.x, -v.y); }
                             else u[bi] = rd[l];
                         } else {
                             int b = rb.first + ib0 + bi; b -= b >= F ? F : 0;
                             const int l = lc + b * MC;
-                            load_filter_vec<MP, GS>(filt + ((size_t)k * MP + l) * GS, w[bi]);
+                            load_filter_vec<MP, GS, FH>(filt + ((size_t)k * MP + l) * GS, w[bi]);
                             if constexpr ((WST_OPT_SPARSEROW & 2) != 0) {
                                 const bool dir = l <= MP / 2;
                                 const cfloat v = dir ? rd[l] : rm[MP - l];
@@ -1238,7 +1307,7 @@ WST_D void product_fold(int tid, const cfloat* uh, const float* filt, int rows, 
             cfloat* op = out + Fft1<MC>::pi(kc) * PC + Fft1<MC>::pi(lc);
             static_for<0, GS>([&](auto G) {
                 constexpr int g = decltype(G)::value;
-                op[g * AS] = cmake(ar[g] * scale, ai[g] * scale);
+                prod_store<OH>(op + g * AS, cmake(ar[g] * scale, ai[g] * scale));
             });
         }
     }
@@ -1472,7 +1541,7 @@ WST_D void ifft_cols_staged(Exec& ex, cfloat* base, int narr, int AS, const cflo
             for (int a = 0; a < na; ++a) {
                 cfloat* dst = base + (g0 + a) * AS + c0 + c;
                 const cfloat* src = buf + a * TILE + c;
-                for (int r = tid / TC; r < M; r += NT / TC) dst[r * P] = src[r * TCP];
+                for (int r = tid / TC; r < M; r += NT / TC) stage_store(dst + r * P, src[r * TCP]);
             }
         });
 }
@@ -1519,7 +1588,7 @@ WST_D void ifft_rows_final_staged(Exec& ex, cfloat* base, int narr, int AS, cons
                 const int row = x0 + (q < TR ? q : q - TR + HALF);
                 cfloat* dst = base + (g0 + a) * AS + row * P;
                 const cfloat* src = buf + a * TILE + q * P;
-                for (int c = tid & 31; c < M; c += 32) dst[c] = src[c];
+                for (int c = tid & 31; c < M; c += 32) stage_store(dst + c, src[c]);
             }
         });
 }
@@ -1737,7 +1806,7 @@ struct Cascade {
         for (int grp = 0; grp < ngroups; ++grp) {
             if (!mine(ubase + grp)) continue;
             ex.template phase<PK_PROD2 * 8 + J2>([&](int tid) {
-                product_fold<MP, MC, G, NT>(tid, uh_parent, pt.psi2[J2][J1] + (size_t)grp * MP * MP * G,
+                product_fold<MP, MC, G, NT, C::WS_GLOBAL && (WST_OPT_L2HINT & 1), glob<J2>() && (WST_OPT_L2HINT & 8)>(tid, uh_parent, pt.psi2[J2][J1] + (size_t)grp * MP * MP * G,
                                             pt.bb2[pair_index(J2, J1)][grp][0], pt.bb2[pair_index(J2, J1)][grp][1], arr);
             });
             ifft2_modulus_lowpass<MC, NT, J2, false, HOUT, HP, C::LP_SLOTS, glob<J2>(), C::stage_cfloats(), C::stage_rows(MC)>(
@@ -1759,7 +1828,7 @@ struct Cascade {
             if constexpr (SPLIT) { first = unit; unit += ntasks; if (!any_mine(first, ntasks)) continue; }
             const bool own_maps = mine(first);                        // the owner of the group's first unit writes S1
             ex.template phase<PK_PROD1 * 8 + J1>([&](int tid) {
-                product_fold<N, M, GPn, NT>(tid, u0h, pt.psi1[J1] + (size_t)grp * N * N * GPn,
+                product_fold<N, M, GPn, NT, C::WS_GLOBAL && (WST_OPT_L2HINT & 1), glob<J1>() && (WST_OPT_L2HINT & 8)>(tid, u0h, pt.psi1[J1] + (size_t)grp * N * N * GPn,
                                             pt.bb1[J1][grp][0], pt.bb1[J1][grp][1], arr);
             });
             ifft2_modulus_lowpass<M, NT, J1, C::has_children(J1), HOUT, HP, C::LP_SLOTS, glob<J1>(), C::stage_cfloats(), C::stage_rows(M)>(

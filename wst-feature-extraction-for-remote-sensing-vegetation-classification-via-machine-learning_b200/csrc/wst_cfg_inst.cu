@@ -47,30 +47,45 @@ __device__ __forceinline__ void run_cascade(Exec& ex, const PlanTables& pt, cons
     prog.mbar = &input_mbar[0];
     prog.load_twiddles();                                // its barrier also publishes the mbarrier initialisation
     if (slot < nsig) prog.prefetch_input(signal_source(in, slot, pt.H, pt.W));
-    for (long long s = slot; s < nsig; s += nslots) {
+    // Signals after a slot's first one are handed out by a device-wide ticket counter (`done`, zeroed by the host)
+    // instead of a fixed stride: SMs do not run at exactly the same speed (distance to the L2 slices that hold the filter
+    // bank, the other die), and over ~80 signals per CTA the static assignment waits for the slowest one.  The ticket of
+    // the following signal is drawn at the top of an iteration, so the input prefetch still knows it one signal ahead.
+    constexpr bool DYN = WST_OPT_DYNSCHED && !SPLIT && C::CL == 1;
+    __shared__ long long next_sig;
+    const bool dyn = DYN && done != nullptr;
+    for (long long s = slot; s < nsig;) {
+        if (dyn) {
+            __syncthreads();                                 // everybody has read the previous ticket
+            if (threadIdx.x == 0) next_sig = (long long)nslots + atomicAdd(done, 1);
+        }                                                    // (published by the first barrier inside run())
         // maps go to the caller's buffer, or to this slot's own (L2-resident) scratch when only features are wanted
         prog.maps = maps_out ? maps_out + (size_t)s * map_elems
                              : maps_scratch + (size_t)(SPLIT ? s : slot) * map_elems;
         auto next = [&](SignalSrc& o) -> bool {
-            if (s + nslots >= nsig) return false;
-            o = signal_source(in, s + nslots, pt.H, pt.W);
+            const long long sn = dyn ? next_sig : s + nslots;
+            if (sn >= nsig) return false;
+            o = signal_source(in, sn, pt.H, pt.W);
             return true;
         };
         auto fptr = [&]() -> float* { return feats ? feats + (size_t)s * 2 * pt.K : nullptr; };
         if constexpr (!SPLIT) {
             prog.run(signal_source(in, s, pt.H, pt.W), fptr, next);
+            s = dyn ? next_sig : s + nslots;
         } else {
             // shared signal: no pooling inside run(); the CTA that finishes last pools from the (L2) maps of all parts
             prog.run(signal_source(in, s, pt.H, pt.W), []() -> float* { return nullptr; }, next);
-            if (!feats) continue;
-            __threadfence();                                 // this thread's map stores are visible device-wide ...
-            __syncthreads();
-            if (threadIdx.x == 0) is_last = atomicAdd(&done[s], 1) == split - 1;     // ... before the CTA checks in
-            __syncthreads();
-            if (is_last) {
-                __threadfence();
-                prog.template pool<true>(fptr());
+            if (feats) {
+                __threadfence();                             // this thread's map stores are visible device-wide ...
+                __syncthreads();
+                if (threadIdx.x == 0) is_last = atomicAdd(&done[s], 1) == split - 1;     // ... before the CTA checks in
+                __syncthreads();
+                if (is_last) {
+                    __threadfence();
+                    prog.template pool<true>(fptr());
+                }
             }
+            s += nslots;
         }
     }
 }
@@ -80,9 +95,9 @@ __device__ __forceinline__ void run_cascade(Exec& ex, const PlanTables& pt, cons
 template <class C>
 __global__ void __launch_bounds__(C::NTL, C::min_ctas())
 cascade_kernel(const __grid_constant__ PlanTables pt, const InputDesc in, long long nsig, cfloat* u0h_scratch,
-               cfloat* workspace, float* maps_out, float* maps_scratch, float* feats) {
+               cfloat* workspace, float* maps_out, float* maps_scratch, float* feats, int* ticket) {
     DevExec<C::CL> ex{C::CL > 1 ? cluster_cta_rank() * C::NTL : 0};
-    run_cascade<C, false>(ex, pt, in, nsig, u0h_scratch, workspace, maps_out, maps_scratch, feats);
+    run_cascade<C, false>(ex, pt, in, nsig, u0h_scratch, workspace, maps_out, maps_scratch, feats, 1, ticket);
 }
 
 // Small-batch twin (shared-memory variant only): `split` CTAs per signal, the last one to finish pools.
@@ -133,7 +148,7 @@ cudaError_t launch_cascade(const PlanTables& pt, const InputDesc& in, long long 
     // slots = CTAs (clusters) in the grid; with split > 1 consecutive groups of `split` CTAs share their signals
     if (split > 1)          // (its shared-memory attribute is set per device by max_slots at plan creation)
         return launch_any<C>(cascade_split_kernel<C>, slots, st, pt, in, nsig, u0h, maps_out, maps_scratch, feats, split, done);
-    return launch_any<C>(cascade_kernel<C>, slots, st, pt, in, nsig, u0h, ws, maps_out, maps_scratch, feats);
+    return launch_any<C>(cascade_kernel<C>, slots, st, pt, in, nsig, u0h, ws, maps_out, maps_scratch, feats, done);
 }
 
 template <class C>

@@ -271,9 +271,19 @@ InputDesc plain_input(const void* ptr, int u8_channels) {
     return in;
 }
 
+// Signals of the ragged last wave that are better run as a split small batch (0: none, or not worth it).
+long long tail_signals(const wst2d_plan* p, long long nsig) {
+    if (p->gen || !p->ops->can_split || nsig <= p->grid_max || getenv("WST_NO_SPLIT") || getenv("WST_NO_TAIL_SPLIT")) return 0;
+    // (over many waves the ticket scheduler already evens the CTAs out and a last wave is a small fraction of the run:
+    // at 84 waves the second launch measured no gain, so it is kept for batches of up to 16 waves)
+    if (nsig > 16ll * p->grid_max) return 0;
+    const long long r = nsig % p->grid_max;
+    return (r > 0 && r * 2 <= p->grid_max) ? r : 0;
+}
+
 int forward_impl(const wst2d_plan* p, const InputDesc& in, long long nsig, float* feats_dev,
                  float* maps_dev, cudaStream_t st, cfloat* own_u0h = nullptr, float* own_maps = nullptr,
-                 cfloat* own_ws = nullptr) {
+                 cfloat* own_ws = nullptr, bool mark = true) {
     if (nsig == 0) return WST2D_OK;
     if (p->gen) {
         std::string err;
@@ -286,6 +296,23 @@ int forward_impl(const wst2d_plan* p, const InputDesc& in, long long nsig, float
     const size_t map_elems = (size_t)p->K * p->hout * p->wout;
     const size_t u0h_elems = (size_t)p->N * (p->N / 2 + 1);
     const size_t ws_elems = p->ops->workspace_cfloats;
+    // Ragged last wave: every signal costs the same and the grid is persistent, so nsig = q * grid + r with a small r
+    // would keep grid - r CTAs idle for a whole signal time.  The r tail signals are run as a small batch instead — a
+    // second launch on the same stream in which each of them is shared among grid / r CTAs (cascade_split_kernel).
+    const long long tail = tail_signals(p, nsig);
+    if (tail > 0) {
+        const long long head = nsig - tail;
+        if (mark) prof_mark(p, p->prof_cascade, st);       // one (start, stop) pair around both launches
+        int rc2 = forward_impl(p, in, head, feats_dev, maps_dev, st, own_u0h, own_maps, own_ws, false);
+        if (rc2 == WST2D_OK) {
+            InputDesc rest = in;
+            rest.sig0 += head;
+            rc2 = forward_impl(p, rest, tail, feats_dev + (size_t)head * 2 * p->K, maps_dev ? maps_dev + (size_t)head * map_elems : nullptr,
+                               st, own_u0h, own_maps, own_ws, false);
+        }
+        if (mark) prof_mark(p, p->prof_cascade, st);
+        return rc2;
+    }
     int grid = (int)(nsig < p->grid_max ? nsig : p->grid_max);
     // small batch: share each signal among `split` CTAs (first-order groups are independent), up to one CTA per group
     int split = 1;
@@ -303,17 +330,21 @@ int forward_impl(const wst2d_plan* p, const InputDesc& in, long long nsig, float
     if (e == cudaSuccess && ws_elems && !d_ws) e = pool_alloc(p, &d_ws, (size_t)grid * ws_elems * sizeof(cfloat), st);
     if (e == cudaSuccess && !maps_dev && !d_maps)
         e = pool_alloc(p, &d_maps, (size_t)(split > 1 ? nsig : grid) * map_elems * sizeof(float), st);
-    if (e == cudaSuccess && split > 1) {
-        e = pool_alloc(p, &d_done, (size_t)nsig * sizeof(int), st);
-        if (e == cudaSuccess) e = cudaMemsetAsync(d_done, 0, (size_t)nsig * sizeof(int), st);
+    // split > 1: per-signal completion counters; otherwise the ticket counter that hands out the signals after each
+    // CTA's first one (more than one wave only; WST_STATIC_SCHED keeps the fixed stride, for A/B runs)
+    const bool tickets = split == 1 && nsig > grid && !getenv("WST_STATIC_SCHED");
+    if (e == cudaSuccess && (split > 1 || tickets)) {
+        const size_t n = split > 1 ? (size_t)nsig : 1;
+        e = pool_alloc(p, &d_done, n * sizeof(int), st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_done, 0, n * sizeof(int), st);
     }
     int rc = WST2D_OK;
     if (e != cudaSuccess) {
         rc = fail(WST2D_ERR_CUDA, std::string("stream-ordered scratch allocation: ") + cudaGetErrorString(e));
     } else {
-        prof_mark(p, p->prof_cascade, st);
+        if (mark) prof_mark(p, p->prof_cascade, st);
         e = p->ops->launch(p->pt, in, nsig, d_u0h, d_ws, maps_dev, maps_dev ? nullptr : d_maps, feats_dev, grid, st, split, d_done);
-        prof_mark(p, p->prof_cascade, st);
+        if (mark) prof_mark(p, p->prof_cascade, st);
         if (e != cudaSuccess) rc = fail(WST2D_ERR_CUDA, std::string("cascade launch: ") + cudaGetErrorString(e));
     }
     if (!own_u0h && d_u0h) cudaFreeAsync(d_u0h, st);
@@ -650,7 +681,8 @@ int wst2d_debug_phase_cycles(const wst2d_plan* p, const float* x_dev, int64_t ns
 int wst2d_launch_count(const wst2d_plan* p, int64_t B, int C) {
     if (!p) return fail(WST2D_ERR_ARG, "plan is NULL");
     if (p->gen) return (int)generic_launch_count(p->gen, (long long)B * C);
-    return (long long)B * C > 0 ? 1 : 0;   // one fused cascade + pooling kernel per forward call
+    if ((long long)B * C <= 0) return 0;
+    return tail_signals(p, (long long)B * C) > 0 ? 2 : 1;   // one fused cascade + pooling kernel per forward call (+ one for a ragged last wave)
 }
 
 int wst2d_debug_num_phase_tags(void) { return kNumPhaseTags; }

@@ -20,7 +20,7 @@ struct CfgOps {
     bool can_split;              // small batches: several CTAs may share one signal (shared-memory variant)
     int (*num_units)(int L, int max_order);   // units of shared work per signal = the largest useful split
     // (tables, input descriptor, nsig, u0h scratch, workspace, maps_out | NULL, maps scratch | NULL, feats | NULL, grid, stream,
-    //  split = CTAs per signal, per-signal completion counters (split > 1))
+    //  split = CTAs per signal, per-signal completion counters (split > 1) | ticket counter or NULL (split == 1))
     cudaError_t (*launch)(const PlanTables&, const InputDesc&, long long, cfloat*, cfloat*, float*, float*, float*, int, cudaStream_t,
                           int, int*);
     cudaError_t (*max_slots)(int device, int* slots);   // signals in flight (resident CTAs or clusters); also sets kernel attributes
