@@ -570,8 +570,16 @@ static int forward_host_impl(const wst2d_plan* p, const void* x_host, bool u8, i
     }
     int rc = WST2D_OK, it = 0;
     const long long nsig = (long long)B * C;
-    for (long long s0 = 0; s0 < nsig && rc == WST2D_OK; s0 += chunk_sig, ++it) {
-        long long n = nsig - s0 < chunk_sig ? nsig - s0 : chunk_sig;
+    // The first copy has nothing to overlap with, so the chunks ramp up: one wave, two waves, then chunk_sig.
+    long long n = 0;
+    for (long long s0 = 0; s0 < nsig && rc == WST2D_OK; s0 += n, ++it) {
+        long long want = chunk_sig;
+        if (!p->gen && it < 2 && !getenv("WST_HOST_NO_RAMP")) {
+            want = (long long)p->grid_max * (it + 1) / C * C;
+            if (want < C) want = C;
+            if (want > chunk_sig) want = chunk_sig;
+        }
+        n = nsig - s0 < want ? nsig - s0 : want;
         int i = it & 1;
         const size_t esz = u8 ? 1 : sizeof(float);      // a chunk is a whole number of patches, so uint8 pixels stay HWC-aligned
         cudaError_t e = cudaMemcpyAsync(hp.x[i], static_cast<const char*>(x_host) + (size_t)s0 * sig_in * esz, n * sig_in * esz,
