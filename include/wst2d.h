@@ -140,8 +140,15 @@ int wst2d_forward_host_u8(const wst2d_plan* plan, const uint8_t* x_host, int64_t
 int wst2d_plan_filters(const wst2d_plan* plan, float* psi_hat, float* phi_hat);
 
 /* Number of kernels wst2d_forward launches for a batch of B*C signals (for launch accounting): the fused cascade
- * pools in-kernel, so this is 1 (wst2d_forward_host launches one per chunk); the GEMM engines launch one kernel per
- * matrix product of the cascade and chunk of signals. */
+ * pools in-kernel, so this is 1 — 2 when the batch is a few persistent-grid waves with a ragged last one, whose
+ * signals then run as a second, split launch (wst2d_forward_host launches that per chunk); the GEMM engines launch one
+ * kernel per matrix product of the cascade and chunk of signals.
+ * Environment knobs read per call, for A/B measurements only (results are bit-identical either way):
+ *   WST_NO_SPLIT=1        never share a signal among CTAs (small batches, ragged last wave)
+ *   WST_NO_TAIL_SPLIT=1   keep small batches split, run a ragged last wave as a whole extra wave
+ *   WST_STATIC_SCHED=1    fixed-stride assignment of signals to CTAs instead of the ticket counter
+ *   WST_HOST_NO_RAMP=1    wst2d_forward_host: equal chunks from the first one on
+ *   WST_HOST_CHUNK_SIGNALS=n   wst2d_forward_host: signals per chunk (default 6 waves) */
 int wst2d_launch_count(const wst2d_plan* plan, int64_t B, int C);
 
 /* Optional per-kernel timing for bench.py's roofline: when enabled, wst2d_forward records CUDA events

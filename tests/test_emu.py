@@ -186,3 +186,52 @@ def test_hybrid_global_workspace_variant_vs_oracle(tmp_path):
         assert rc == 0
         assert not np.isnan(out).any() and floored_rel(out, ref) <= 1e-4 / 4, (M, J)
         assert floored_rel(feats[:, 0], ref.mean(axis=(-2, -1))) <= 1e-4 / 4
+
+
+def test_fused_product_tile_vs_oracle(tmp_path):
+    """WST_OPT_PRODTILE (the 256 x 256 builds): workspace-level arrays with fold factor <= 2 get their filter product
+    computed straight into the shared-memory column tile of the inverse transform; the workspace then holds natural-order
+    columns between the column and the row passes.  Replayed at small sides: first-order products without fold (80, 136,
+    160) and with fold 2, second-order children with fold 2 (eight- and four-column tiles of four and eight arrays),
+    Cooley-Tukey and Good-Thomas lengths; same numbers as the unfused build to rounding."""
+    import ctypes
+    import subprocess
+
+    def build(tag, cfgs, defs):
+        inc = tmp_path / (tag + ".inc")
+        inc.write_text("".join("CFGG(%d, %d)\n" % c for c in cfgs))
+        lib_path = tmp_path / ("libwst_emu_%s.so" % tag)
+        subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared"] + defs + ["-DWST_EMU_CONFIG_FILE=\"%s\"" % inc.name,
+                        "-I", str(tmp_path), "-I", emu.CSRC, "-I", emu.HERE, emu.HERE + "/wst_emu.cpp", "-o", str(lib_path)],
+                       check=True)
+        lib = ctypes.CDLL(str(lib_path))
+        lib.emu_forward.argtypes = [ctypes.c_int] * 6 + [ctypes.c_void_p] * 3 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        return lib
+
+    def run(lib, M, J, L, N):
+        rng = np.random.default_rng(N + 7)
+        x = (rng.integers(0, 256, (1, M, M)) / 255.0).astype(np.float32)
+        S = Scattering2D(J=J, shape=(M, M), L=L, precision="double", cache_filters=True)
+        assert S._M_padded == N
+        psi = np.ascontiguousarray(np.stack([p["levels"][0] for p in S.psi]), np.float32)
+        phi = np.ascontiguousarray(S.phi["levels"][0], np.float32)
+        ref = S(x)
+        K, h = ref.shape[1], N // 2 ** J - 2
+        out = np.full((1, K, h, h), np.nan, np.float32)
+        feats = np.full((1, 2, K), np.nan, np.float32)
+        rc = lib.emu_forward(N, J, L, 2, M, M, psi.ctypes.data, phi.ctypes.data, x.ctypes.data, 1, out.ctypes.data,
+                             feats.ctypes.data)
+        assert rc == 0 and not np.isnan(out).any()
+        return out, ref
+
+    glob = [(80, 3), (136, 2), (48, 3)]
+    fused = build("pt1", glob, ["-DWST_OPT_PRODTILE=1", "-DWST_GLOBAL_BUDGET=32768"])
+    plain = build("pt0", glob, ["-DWST_OPT_PRODTILE=0", "-DWST_GLOBAL_BUDGET=32768"])
+    for M, J, L, N in [(64, 3, 8, 80), (128, 2, 8, 136), (32, 3, 6, 48)]:
+        a, ref = run(fused, M, J, L, N)
+        b, _ = run(plain, M, J, L, N)
+        assert floored_rel(a, ref) <= 1e-4 / 4, (M, J)
+        assert np.abs(a - b).max() <= 1e-6 * np.abs(b).max(), (M, J)
+    hyb = build("pt1h", [(160, 4)], ["-DWST_OPT_PRODTILE=1", "-DWST_GLOBAL_BUDGET=65536", "-DWST_HYBRID_BUDGET=4000"])
+    a, ref = run(hyb, 128, 4, 8, 160)
+    assert floored_rel(a, ref) <= 1e-4 / 4

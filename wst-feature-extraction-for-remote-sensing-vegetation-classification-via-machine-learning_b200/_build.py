@@ -36,7 +36,11 @@ GLOBAL_VARIANT_HYBRID = int(os.environ.get("WST_BUILD_HYBRID", 0))
 SHARED_OVERRIDES = {(40, 2): (160, 6000), (80, 3): (320, 12000)}     # four / two narrower CTAs per SM (measured best)
 # Per-configuration tuning knobs of csrc/wst_cascade.h that measured better for that configuration only
 # (the sparse / dense-many products with hoisted spectrum rows: +2.4 % at 64x64 J=3, -1.2 % at 128x128 J=4)
-CONFIG_DEFS = {(80, 3): ["-DWST_OPT_SPARSEROW=7"]}
+# (the filter product fused into the column tile of the inverse transform: +1.9 % at 256x256 J=4, where only level 0 lives
+# in the workspace; -1.8 % at 512x512 J=5, whose 288^2 / 144^2 children get four- and eight-column tiles)
+CONFIG_DEFS = {(80, 3): ["-DWST_OPT_SPARSEROW=7"],
+               (264, 2): ["-DWST_OPT_PRODTILE=1"], (272, 3): ["-DWST_OPT_PRODTILE=1"], (288, 4): ["-DWST_OPT_PRODTILE=1"],
+               (320, 5): ["-DWST_OPT_PRODTILE=1"]}
 for _item in filter(None, os.environ.get("WST_BUILD_SHARED", "").split(",")):
     _n, _j, _t, _b = (int(v) for v in _item.split(":"))
     SHARED_OVERRIDES[(_n, _j)] = (_t, _b)

@@ -214,11 +214,25 @@ WST_CX bool lp_banded(int m, int hout, int level) {
 #ifndef WST_OPT_DYNSCHED
 #define WST_OPT_DYNSCHED 1
 #endif
+//   WST_OPT_PRODTILE  global-workspace levels with fold factor <= 2: the filter product is computed straight into the
+//                     shared-memory column tile that the inverse column transforms run on (product_ifft_cols_staged)
+//                     instead of being written to the workspace and loaded back tile by tile: one write and one read
+//                     of every such array less.  The workspace then holds the array with its columns in natural
+//                     frequency order between the column and the row passes (the row-tile loads permute).
+#ifndef WST_OPT_PRODTILE
+#define WST_OPT_PRODTILE 0
+#endif
 #ifndef WST_STAGE_TC_MAX
 #define WST_STAGE_TC_MAX 16
 #endif
 // columns per staged tile of the global-workspace variant: the largest power of two <= WST_STAGE_TC_MAX dividing m
 WST_CX int stage_tc(int m) { int t = WST_STAGE_TC_MAX; while (m % t) t /= 2; return t; }
+// columns per tile of the fused product + column transform: gs arrays of mc rows, pitch t + 1, in `avail` cfloats
+// (0: does not fit with at least four columns — a row segment of a tile store is then a whole 32-byte sector)
+WST_CX int prodtile_cols(int mc, int gs, int avail) {
+    for (int t = 16; t >= 4; t /= 2) if (mc % t == 0 && gs * mc * (t + 1) <= avail) return t;
+    return 0;
+}
 
 // ------------------------------------------------------------------ geometry shared by host and device
 // WS_GLOBAL = false: the data region lives in shared memory (the fast path, N <= 160).
@@ -354,6 +368,8 @@ struct Cfg {
     // batch of row pairs) so that each array crosses HBM once per dimension instead of once per pass.
     static WST_CX int stage_cols(int m) { return stage_tc(m); }                                 // columns per tile
     static WST_CX int stage_cfloats() { return WS_GLOBAL ? N * (stage_cols(N) + 1) : 0; }      // one level-0 column tile
+    // shared memory behind `stage`: the stage tiles and the hybrid region alias each other
+    static WST_CX int stage_avail() { return WS_GLOBAL ? cx_max(WST_STAGE_BUFS * stage_cfloats(), hybrid_cfloats()) : 0; }
     static constexpr int STAGE_BUFS = WST_STAGE_BUFS;   // 2: tile t+1 is loaded (asynchronously) while tile t is transformed
     static WST_CX int stage_rows(int m) {                                                       // row pairs per tile
         int t = 16;
@@ -1546,7 +1562,9 @@ WST_D void ifft_cols_staged(Exec& ex, cfloat* base, int narr, int AS, const cflo
         });
 }
 
-template <int M, int NT, int STAGE, int TR, bool WRITE_Z, bool LPF, int HOUT, int HP, int LV, class Exec>
+// NATCOL: the workspace holds the columns in natural frequency order (written by product_ifft_cols_staged); the tile
+// loads put column l at its transform position pi(l).
+template <int M, int NT, int STAGE, int TR, bool WRITE_Z, bool LPF, int HOUT, int HP, int LV, bool NATCOL = false, class Exec>
 WST_D void ifft_rows_final_staged(Exec& ex, cfloat* base, int narr, int AS, const cfloat* tw, const float* g,
                                   cfloat* stage) {
     constexpr int P = M + 1, HALF = M / 2, TILE = 2 * TR * P, NX = HALF / TR;
@@ -1567,6 +1585,8 @@ WST_D void ifft_rows_final_staged(Exec& ex, cfloat* base, int narr, int AS, cons
                 const int row = x0 + (q < TR ? q : q - TR + HALF);
                 const cfloat* src = base + (g0 + a) * AS + row * P;
                 cfloat* dst = buf + a * TILE + q * P;
+                if constexpr (NATCOL) { for (int c = tid & 31; c < M; c += 32) stage_copy(dst + Fft1<M>::pi(c), src + c); }
+                else
                 for (int c = tid & 31; c < M; c += 32) stage_copy(dst + c, src + c);
             }
         },
@@ -1593,22 +1613,80 @@ WST_D void ifft_rows_final_staged(Exec& ex, cfloat* base, int narr, int AS, cons
         });
 }
 
+// Global-workspace levels, fold factor F <= 2: V_g = fold(U . psi_g) for the GS filters of a group computed straight into
+// a shared-memory tile of TCF natural-frequency columns (all MC rows, all GS arrays), transformed along the columns there
+// and stored to the workspace once — the array skips one write and one read (the product_fold output and the column-tile
+// load of ifft_cols_staged).  Rows of the tile are in transform order pi(k); the columns go to the workspace in natural
+// order l0 .. l0 + TCF - 1 (whole 32-byte sectors), which the row-tile loads of ifft_rows_final_staged<NATCOL> undo.
+// Same accumulation order as product_fold's dense branches (aliases a-major).
+template <int MP, int MC, int GS, int NT, int AVAIL, int LV, int TAG_PROD, bool FH, class Exec>
+WST_D void product_ifft_cols_staged(Exec& ex, const cfloat* uh, const float* filt, cfloat* base, const cfloat* tw,
+                                    cfloat* stage) {
+    constexpr int F = MP / MC, P = MC + 1, AS = MC * (MC + 1);
+    constexpr int TCF = prodtile_cols(MC, GS, AVAIL), TCP = TCF + 1, TILE = MC * TCP, NCT = MC / TCF;
+    constexpr bool TWO = Fft1<MC>::R1 > 1;
+    constexpr float scale = 1.0f / ((float)F * (float)F * (float)MC * (float)MC);
+    static_assert(F <= 2 && TCF >= 4, "fused product tile: fold factor <= 2 and at least four columns");
+    for (int t = 0; t < NCT; ++t) {
+        const int l0 = t * TCF;
+        ex.template phase<TAG_PROD * 8 + LV>([&](int tid) {
+            for (int o = tid; o < MC * TCF; o += NT) {
+                const int c = o % TCF, kc = o / TCF, lc = l0 + c;
+                float w[F * F][GS];
+                cfloat u[F * F];
+                static_for<0, F * F>([&](auto S) {
+                    constexpr int sl = decltype(S)::value;
+                    const int k = kc + (sl / F) * MC, l = lc + (sl % F) * MC;
+                    load_filter_vec<MP, GS, FH>(filt + ((size_t)k * MP + l) * GS, w[sl]);
+                    u[sl] = herm_get<MP>(uh, k, l);
+                });
+                float ar[GS], ai[GS];
+                static_for<0, GS>([&](auto G) { ar[decltype(G)::value] = 0.f; ai[decltype(G)::value] = 0.f; });
+                static_for<0, F * F>([&](auto S) {
+                    constexpr int sl = decltype(S)::value;
+                    static_for<0, GS>([&](auto G) {
+                        constexpr int g = decltype(G)::value;
+                        ar[g] += u[sl].x * w[sl][g];
+                        ai[g] += u[sl].y * w[sl][g];
+                    });
+                });
+                cfloat* op = stage + Fft1<MC>::pi(kc) * TCP + c;
+                static_for<0, GS>([&](auto G) {
+                    constexpr int g = decltype(G)::value;
+                    op[g * TILE] = cmake(ar[g] * scale, ai[g] * scale);
+                });
+            }
+        });
+        ex.template phase<PK_IFFT_COL_C * 8 + LV>([&](int tid) { pass_contig<MC, +1, true, TCF, 1, TCP, NT>(tid, stage, GS, TILE, tw); });
+        if constexpr (TWO)
+            ex.template phase<PK_IFFT_COL_S * 8 + LV>([&](int tid) { pass_strided<MC, +1, false, TCF, 1, TCP, NT>(tid, stage, GS, TILE, tw); });
+        ex.template phase<PK_STAGE_ST * 8 + LV>([&](int tid) {
+            for (int o = tid; o < GS * MC * TCF; o += NT) {
+                const int c = o % TCF, r = (o / TCF) % MC, g = o / (TCF * MC);
+                stage_store(base + g * AS + r * P + l0 + c, stage[g * TILE + r * TCP + c]);
+            }
+        });
+    }
+}
+
 // Inverse 2-D FFT of narr digit-swapped M x M spectra (pitch M+1) + modulus (+ row-paired z for a following
 // rfft2_from_pairs) + low-pass map of every array.
+// COLS_DONE: the column transforms have already run (product_ifft_cols_staged) and the columns are in natural order.
 template <int M, int NT, int LV, bool WRITE_Z, int HOUT, int HP, int LPSLOTS, bool GLOB = false, int STAGE = 0, int TR = 1,
-          class Exec, class CoefFn>
+          bool COLS_DONE = false, class Exec, class CoefFn>
 WST_D void ifft2_modulus_lowpass(Exec& ex, cfloat* base, int narr, const cfloat* tw, const float* g,
                                  const float (&w)[kLpTaps], float* lpbuf, float* maps, cfloat* stage, CoefFn coef) {
     constexpr int P = M + 1, AS = M * (M + 1);
     constexpr bool FUSED = (Fft1<M>::R1 == 1) ? !WRITE_Z
                                               : (WRITE_Z ? (HOUT <= Fft1<M>::R1) : (HOUT / 2 <= Fft1<M>::R1));
     if constexpr (GLOB && STAGE > 0) {
-        ifft_cols_staged<M, NT, STAGE, LV>(ex, base, narr, AS, tw, stage);
-        ifft_rows_final_staged<M, NT, STAGE, TR, FUSED ? WRITE_Z : true, FUSED, HOUT, HP, LV>(ex, base, narr, AS, tw, g, stage);
+        if constexpr (!COLS_DONE) ifft_cols_staged<M, NT, STAGE, LV>(ex, base, narr, AS, tw, stage);
+        ifft_rows_final_staged<M, NT, STAGE, TR, FUSED ? WRITE_Z : true, FUSED, HOUT, HP, LV, COLS_DONE>(ex, base, narr, AS, tw, g, stage);
         if constexpr (FUSED) lowpass_reduce<M, NT, WRITE_Z, HOUT, HP, LPSLOTS, LV>(ex, base, narr, AS, g, lpbuf, maps, coef);
         else lowpass_maps<M, HOUT, HP, NT, LV, false>(ex, base, AS, narr, g, g, w, maps, coef);
         return;
     }
+    // (COLS_DONE only comes with GLOB && STAGE > 0: the branch above)
     fft_lines_inv<M, M, 1, P, NT, PK_IFFT_COL_C * 8 + LV, PK_IFFT_COL_S * 8 + LV>(ex, base, narr, AS, tw);   // columns
     if constexpr (Fft1<M>::R1 > 1) {
         ex.template phase<PK_IFFT_ROW_C * 8 + LV>([&](int tid) { pass_contig<M, +1, true, M, P, 1, NT, GLOB>(tid, base, narr, AS, tw); });
@@ -1805,11 +1883,18 @@ struct Cascade {
         cfloat* arr = base<J2>();
         for (int grp = 0; grp < ngroups; ++grp) {
             if (!mine(ubase + grp)) continue;
+            // fused product + column transforms on a shared-memory tile (workspace-level children, fold factor <= 2)
+            constexpr bool PT = WST_OPT_PRODTILE && C::CL == 1 && glob<J2>() && C::stage_cfloats() > 0 && MP / MC <= 2 &&
+                                prodtile_cols(MC, G, C::stage_avail()) > 0;
+            if constexpr (PT) {
+                product_ifft_cols_staged<MP, MC, G, NT, C::stage_avail(), J2, PK_PROD2, (WST_OPT_L2HINT & 1) != 0>(
+                    ex, uh_parent, pt.psi2[J2][J1] + (size_t)grp * MP * MP * G, arr, tw(J2), stage);
+            } else
             ex.template phase<PK_PROD2 * 8 + J2>([&](int tid) {
                 product_fold<MP, MC, G, NT, C::WS_GLOBAL && (WST_OPT_L2HINT & 1), glob<J2>() && (WST_OPT_L2HINT & 8)>(tid, uh_parent, pt.psi2[J2][J1] + (size_t)grp * MP * MP * G,
                                             pt.bb2[pair_index(J2, J1)][grp][0], pt.bb2[pair_index(J2, J1)][grp][1], arr);
             });
-            ifft2_modulus_lowpass<MC, NT, J2, false, HOUT, HP, C::LP_SLOTS, glob<J2>(), C::stage_cfloats(), C::stage_rows(MC)>(
+            ifft2_modulus_lowpass<MC, NT, J2, false, HOUT, HP, C::LP_SLOTS, glob<J2>(), C::stage_cfloats(), C::stage_rows(MC), PT>(
                 ex, arr, G, tw(J2), g(J2), pt.lpw[J2], lpbuf, maps, stage,
                 [&](int a) { int t2 = grp * G + a; return t2 < L ? cbase + t2 : -1; });
         }
@@ -1827,11 +1912,17 @@ struct Cascade {
             int first = 0;
             if constexpr (SPLIT) { first = unit; unit += ntasks; if (!any_mine(first, ntasks)) continue; }
             const bool own_maps = mine(first);                        // the owner of the group's first unit writes S1
+            constexpr bool PT = WST_OPT_PRODTILE && C::CL == 1 && glob<J1>() && C::stage_cfloats() > 0 && N / M <= 2 &&
+                                prodtile_cols(M, GPn, C::stage_avail()) > 0;
+            if constexpr (PT) {
+                product_ifft_cols_staged<N, M, GPn, NT, C::stage_avail(), J1, PK_PROD1, (WST_OPT_L2HINT & 1) != 0>(
+                    ex, u0h, pt.psi1[J1] + (size_t)grp * N * N * GPn, arr, tw(J1), stage);
+            } else
             ex.template phase<PK_PROD1 * 8 + J1>([&](int tid) {
                 product_fold<N, M, GPn, NT, C::WS_GLOBAL && (WST_OPT_L2HINT & 1), glob<J1>() && (WST_OPT_L2HINT & 8)>(tid, u0h, pt.psi1[J1] + (size_t)grp * N * N * GPn,
                                             pt.bb1[J1][grp][0], pt.bb1[J1][grp][1], arr);
             });
-            ifft2_modulus_lowpass<M, NT, J1, C::has_children(J1), HOUT, HP, C::LP_SLOTS, glob<J1>(), C::stage_cfloats(), C::stage_rows(M)>(
+            ifft2_modulus_lowpass<M, NT, J1, C::has_children(J1), HOUT, HP, C::LP_SLOTS, glob<J1>(), C::stage_cfloats(), C::stage_rows(M), PT>(
                 ex, arr, GPn, tw(J1), g(J1), pt.lpw[J1], lpbuf, maps, stage,
                 [&](int a) { int t1 = grp * GPn + a; return (t1 < L && own_maps) ? 1 + J1 * L + t1 : -1; });
             if constexpr (C::has_children(J1)) {
