@@ -193,7 +193,8 @@ def test_fused_product_tile_vs_oracle(tmp_path):
     computed straight into the shared-memory column tile of the inverse transform; the workspace then holds natural-order
     columns between the column and the row passes.  Replayed at small sides: first-order products without fold (80, 136,
     160) and with fold 2, second-order children with fold 2 (eight- and four-column tiles of four and eight arrays),
-    Cooley-Tukey and Good-Thomas lengths; same numbers as the unfused build to rounding."""
+    Cooley-Tukey and Good-Thomas lengths (the unfused build of the same configurations is
+    test_global_workspace_variant_vs_oracle; the two agree to rounding, profiles/r02_prodtile_ab.txt)."""
     import ctypes
     import subprocess
 
@@ -226,12 +227,70 @@ def test_fused_product_tile_vs_oracle(tmp_path):
 
     glob = [(80, 3), (136, 2), (48, 3)]
     fused = build("pt1", glob, ["-DWST_OPT_PRODTILE=1", "-DWST_GLOBAL_BUDGET=32768"])
-    plain = build("pt0", glob, ["-DWST_OPT_PRODTILE=0", "-DWST_GLOBAL_BUDGET=32768"])
     for M, J, L, N in [(64, 3, 8, 80), (128, 2, 8, 136), (32, 3, 6, 48)]:
         a, ref = run(fused, M, J, L, N)
-        b, _ = run(plain, M, J, L, N)
         assert floored_rel(a, ref) <= 1e-4 / 4, (M, J)
-        assert np.abs(a - b).max() <= 1e-6 * np.abs(b).max(), (M, J)
     hyb = build("pt1h", [(160, 4)], ["-DWST_OPT_PRODTILE=1", "-DWST_GLOBAL_BUDGET=65536", "-DWST_HYBRID_BUDGET=4000"])
     a, ref = run(hyb, 128, 4, 8, 160)
     assert floored_rel(a, ref) <= 1e-4 / 4
+
+
+def test_shipped_global_workspace_builds_under_asan(tmp_path):
+    """The 256 x 256 / 224 x 224 / 512 x 512 cascades exactly as `_build.py` ships them (threads per CTA, hybrid
+    shared-memory budget, workspace budget, per-configuration knobs such as the fused product tile), replayed with
+    AddressSanitizer and exact-size buffers (workspace, stage / hybrid region, tables are separate heap blocks) against
+    the float64 oracle: the bounds check compute-sanitizer would do on the GPU pool, where it is not available."""
+    import concurrent.futures
+    import importlib
+    import os
+    import subprocess
+    import sys
+    b = importlib.import_module("wst_b200._build")
+    sizes = {(264, 2): 256, (272, 3): 256, (288, 4): 256, (320, 5): 256, (240, 3): 224, (576, 5): 512}
+    src = open(os.path.join(emu.HERE, "wst_emu.cpp")).read().replace("C::smem_cfloats() + 64", "C::smem_cfloats()")
+    assert "Cfg<n, j, 256, true>" in src
+
+    def build(item):
+        (N, J), (nt, hyb, budget) = item
+        cpp = tmp_path / ("emu_%d_%d.cpp" % (N, J))
+        cpp.write_text(src.replace("Cfg<n, j, 256, true>", "Cfg<n, j, %d, true>" % nt))
+        (tmp_path / ("c_%d_%d.inc" % (N, J))).write_text("CFGG(%d, %d)\n" % (N, J))
+        lib = tmp_path / ("libwst_emu_asan_%d_%d.so" % (N, J))
+        subprocess.run(["g++", "-std=c++17", "-O1", "-fsanitize=address", "-fno-omit-frame-pointer", "-fPIC", "-shared",
+                        "-DWST_GLOBAL_BUDGET=%d" % budget, "-DWST_HYBRID_BUDGET=%d" % hyb] + b.CONFIG_DEFS.get((N, J), []) +
+                       ["-DWST_EMU_CONFIG_FILE=\"c_%d_%d.inc\"" % (N, J), "-I", str(tmp_path), "-I", emu.CSRC, "-I", emu.HERE,
+                        str(cpp), "-o", str(lib)], check=True)
+        return (N, J), lib
+
+    items = sorted(b.GLOBAL_OVERRIDES.items())
+    assert set(k for k, _ in items) == set(sizes), "a shipped global-workspace configuration has no emulator case"
+    if not os.environ.get("WST_SLOW_TESTS"):     # all six take 3.5 minutes (the sanitised compiles): by default the two
+        items = [it for it in items if it[0] in ((288, 4), (320, 5))]   # builds with the widest CTAs and the fused product tile
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(items), os.cpu_count() or 2)) as ex:
+        libs = list(ex.map(build, items))
+    asan = subprocess.run(["g++", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    # the sanitised child only replays the kernel: filter bank, input and reference are prepared here, without ASAN
+    code = (
+        "import ctypes, numpy as np, sys\n"
+        "lib = ctypes.CDLL(sys.argv[1]); d = np.load(sys.argv[2]); N, J, L, M, K, h = (int(v) for v in d['geom'])\n"
+        "lib.emu_forward.argtypes = [ctypes.c_int] * 6 + [ctypes.c_void_p] * 3 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]\n"
+        "psi, phi, x = (np.ascontiguousarray(d[k], np.float32) for k in ('psi', 'phi', 'x'))\n"
+        "out = np.empty((1, K, h, h), np.float32); f = np.empty((1, 2, K), np.float32)\n"
+        "rc = lib.emu_forward(N, J, L, 2, M, M, psi.ctypes.data, phi.ctypes.data, x.ctypes.data, 1, out.ctypes.data, f.ctypes.data)\n"
+        "assert rc == 0 and np.isfinite(out).all() and np.isfinite(f).all()\n"
+        "np.save(sys.argv[3], out)\n"
+        "print('clean')\n")
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0")
+    for (N, J), lib in libs:
+        M, L = sizes[(N, J)], 8
+        S = Scattering2D(J=J, shape=(M, M), L=L, precision="double", cache_filters=True)
+        assert S._M_padded == N
+        x = (np.random.default_rng(N).integers(0, 256, (1, M, M)) / 255.0).astype(np.float32)
+        K, h = 1 + L * J + L * L * J * (J - 1) // 2, N // 2 ** J - 2
+        inp, outp = tmp_path / ("in_%d_%d.npz" % (N, J)), tmp_path / ("out_%d_%d.npy" % (N, J))
+        np.savez(inp, psi=np.stack([q["levels"][0] for q in S.psi]).astype(np.float32), phi=S.phi["levels"][0].astype(np.float32),
+                 x=x, geom=np.array([N, J, L, M, K, h]))
+        r = subprocess.run([sys.executable, "-c", code, str(lib), str(inp), str(outp)], capture_output=True, text=True, env=env)
+        assert r.returncode == 0 and "clean" in r.stdout, "(%d, %d): " % (N, J) + r.stdout[-2000:] + r.stderr[-4000:]
+        if M <= 256:                     # (512 x 512 parity is a GPU test; here it is the bounds that are checked)
+            assert floored_rel(np.load(outp), S(x)) <= 1e-4 / 4, (N, J)
